@@ -1,0 +1,427 @@
+#!/usr/bin/env python3
+"""Benchmark of the two-site DMRG hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--chi 2048] [--dtype f64|c128]
+
+Workload (config.workload): BASELINE config 3 -- Heisenberg chain L=100, chi=2048, the bulk bond (sites 50|51),
+MPO bond W=5, d=2.  A *step* is one H_eff matvec  out = L . M1 . M2 . R . theta  (reference
+quantum_simulation/dmrg.py:178-228, the operator Lanczos applies 8x per bond update).
+
+  value        whole-job matvec throughput in GFLOP/s with every input resident in HBM, counted with the dense
+               ncon-order flop count the reference executes (qsb_heff_flops)
+  e2e          the same metric through the reference-facing call ``ApplyMPO.forward`` with theta in pinned HOST
+               memory: H2D copy of theta + matvec + D2H copy of the result inside the timed region
+  roofline     the dominant kernel (the FP64 tensor-core GEMM of step 1), timed with CUDA events recorded on the
+               launching stream inside the timed region (qsb_heff_set_stage_events); peak = FP64 tensor-pipe
+               issue rate measured in this run by the register-resident DMMA probe (MEASURED_PEAKS.json has no
+               FP64 entry); cuBLAS DGEMM 8192^3 and the same matvec run by torch/cuBLAS on this GPU are reported
+               beside it
+  cpu_baseline the oracle (torch-CPU restatement of the reference's ncon path) timed on the host cores
+  lanczos / env_update   the other hot-path kernels: achieved HBM GB/s of the fused vector ops, env-update GFLOP/s
+
+N > 1: the matvec is sharded over the left bond index a' (rows of L and of the result); every step all-gathers
+theta across the ranks (NCCL) and runs the local row block -- strong scaling of the same chi.
+``--impl reference`` times the oracle on the host cores (rank 0 only) for the same config.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "H_eff matvec throughput (DMRG two-site, Heisenberg L=100 bulk bond)"
+UNIT = "GFLOP/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--chi", type=int, default=2048)
+    ap.add_argument("--dtype", default="f64", choices=["f64", "c128"])
+    ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / lanczos / env / library legs")
+    return ap.parse_args()
+
+
+def load_mpo(key, dtype):
+    z = np.load(os.path.join(ROOT, "tests", "golden", "mpo.npz"))
+    return [torch.from_numpy(z[f"{key}/t{int(u)}"]).to(dtype).contiguous() for u in z[f"{key}/index"]]
+
+
+def make_inputs(chi, dtype, device, rows=None, row0=0):
+    """Seeded synthetic bulk-bond inputs: real MPO site tensors of the model, random L/R/theta.
+    Generated per row so that any row shard sees exactly the rows of the global problem."""
+    key = "heis_f64_L100" if dtype == torch.float64 else "heis_c128_L100"
+    mpo = load_mpo(key, dtype)
+    M1, M2 = mpo[50].to(device), mpo[51].to(device)
+    W = M1.shape[0]
+    g = torch.Generator(device="cpu").manual_seed(0)
+    rows = chi if rows is None else rows
+    gl = torch.Generator(device=device).manual_seed(1000 + row0)
+    L = torch.randn(W, rows, chi, dtype=dtype, device=device, generator=gl) / chi ** 0.5
+    gr = torch.Generator(device=device).manual_seed(1)
+    R = torch.randn(M2.shape[1], chi, chi, dtype=dtype, device=device, generator=gr) / chi ** 0.5
+    gt = torch.Generator(device=device).manual_seed(2)
+    theta = torch.randn(chi * M1.shape[3] * M2.shape[3] * chi, dtype=dtype, device=device, generator=gt)
+    theta /= torch.linalg.norm(theta)
+    return L, M1, M2, R, theta
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+            except Exception:
+                continue
+            for nm, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_setup(n):
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm: the oracle (torch-CPU restatement of the reference's ncon path) on the host cores
+# ----------------------------------------------------------------------------------------------
+def cpu_matvec_time(chi, dtype, reps, rows=None, threads=None):
+    from oracle import dmrg_oracle as orc
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    L, M1, M2, R, theta = make_inputs(chi, dtype, "cpu", rows=rows)
+    flops = orc.matvec_flops(L, M1, M2, R)
+    out = torch.empty(L.shape[1] * M1.shape[2] * M2.shape[2] * R.shape[1], dtype=dtype)
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        orc.apply_mpo(theta, L, M1, M2, R, out=out)
+        ts.append(time.perf_counter() - t0)
+    return ts, flops, threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    dtype = torch.float64 if args.dtype == "f64" else torch.complex128
+    cores = os.cpu_count() or 1
+    # one full-size matvec decides the bounded sample: a block of `rows` left-bond rows of the same problem
+    ts, flops_full, threads = cpu_matvec_time(args.chi, dtype, 1)
+    budget = 200.0
+    total_steps = args.steps + args.warmup
+    frac = min(1.0, budget / max(ts[0] * total_steps, 1e-9))
+    rows = max(64, int(args.chi * frac) // 64 * 64) if frac < 1.0 else args.chi
+    rows = min(rows, args.chi)
+    ts, flops, _ = cpu_matvec_time(args.chi, dtype, total_steps, rows=rows)
+    timed = ts[args.warmup:]
+    sec = sum(timed) / len(timed)
+    val = flops / sec / 1e9
+    sample = (f"rows [0,{rows}) of the left bond (of {args.chi}) of the same chi={args.chi} matvec per step, "
+              f"{len(timed)} timed steps, oracle ncon-order tensordots on torch CPU ({torch.__config__.parallel_info().splitlines()[0]})")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": workload_config(args, 1),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(args, world):
+    return {"workload": f"BASELINE config 3: Heisenberg chain L=100, chi={args.chi}, bulk bond 50|51, W=5, d=2, "
+                        f"{'float64 (real Sp/Sm/Sz MPO)' if args.dtype == 'f64' else 'complex128 (stock Sx/Sy/Sz MPO)'}; "
+                        "one H_eff matvec per step",
+            "chi": args.chi, "d": 2, "W": 5, "L": 100,
+            "parallelism": "single GPU" if world == 1 else f"left-bond row shards x{world} + theta all-gather",
+            "l2_policy": "inputs + intermediates per step (>1 GB at chi=2048) exceed the 126 MB L2; no flush needed"}
+
+
+# ----------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------
+def time_region(fn, steps):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    e1.synchronize()
+    return e0.elapsed_time(e1) * 1e-3
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    import quantum_simulation_b200 as qsb
+    from quantum_simulation_b200 import _lib
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    rank, world, local = dist_setup(args.gpus)
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    dtype = torch.float64 if args.dtype == "f64" else torch.complex128
+    es = 8 if dtype == torch.float64 else 16
+    chi = args.chi
+    assert chi % world == 0
+    rows = chi // world
+    L, M1, M2, R, theta = make_inputs(chi, dtype, dev, rows=rows, row0=rank * rows)
+    n = theta.numel()
+    n_loc = rows * M1.shape[2] * M2.shape[2] * chi
+    op = qsb.ApplyMPO("ncon")
+    out = torch.empty(n_loc, dtype=dtype, device=dev)
+    flops_local = _lib.heff_flops(theta, L, M1, M2, R)
+    flops_total = flops_local * world
+
+    theta_shard = theta.view(world, -1)[rank].clone() if world > 1 else None
+
+    def step():
+        if world > 1:      # the exchange step of the sharded matvec: block all-gather of theta
+            dist.all_gather_into_tensor(theta, theta_shard)
+        op(theta, L, M1, M2, R, out=out)
+
+    # ---- FP64 tensor-pipe peak of this GPU, measured now (no FP64 entry in MEASURED_PEAKS.json)
+    peak_tf = _lib.probe_dmma_tflops()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+
+    # ---- timed region: exactly K steps, stage events on the launching stream, clocks sampled meanwhile
+    K = args.steps
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
+    for row in evs:
+        for e in row:
+            e.record()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    _lib.launch_counters(reset=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        _lib.set_stage_events(evs[i])
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    _lib.set_stage_events(None)
+    sec = e0.elapsed_time(e1) * 1e-3
+    launches = _lib.launch_counters()
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([sec], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sec = float(t.item())
+    ms_step = sec / K * 1e3
+    value = flops_total / (sec / K) / 1e9
+
+    g1 = [evs[i][0].elapsed_time(evs[i][1]) for i in range(K)]
+    mix = [evs[i][1].elapsed_time(evs[i][2]) for i in range(K)]
+    g4 = [evs[i][2].elapsed_time(evs[i][3]) for i in range(K)]
+    c = 8.0 if dtype.is_complex else 2.0
+    W, d2 = M1.shape[0], M1.shape[3] * M2.shape[3]
+    g1_flops = c * W * rows * chi * d2 * chi            # step-1 GEMM: algorithmic flops per launch
+    g4_flops = c * chi * (M2.shape[1] * chi) * (M1.shape[2] * M2.shape[2] * rows)
+    g1_ms = sum(g1) / K
+    achieved = g1_flops / (g1_ms * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": "gemm (FP64 DMMA), H_eff step 1", "achieved": achieved,
+                "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
+                "traffic": None,
+                "peak_source": "measured in this run: register-resident mma.sync.m8n8k4.f64 issue-rate probe "
+                               "(qsb_probe_dmma); MEASURED_PEAKS.json has no FP64 entry",
+                "algorithmic_flops_per_launch": g1_flops, "avg_launch_ms": g1_ms,
+                "stage_ms": {"gemm_step1": g1_ms, "mpo_mix": sum(mix) / K, "gemm_step4": sum(g4) / K},
+                "step4_tflops": g4_flops / (sum(g4) / K * 1e-3) / 1e12,
+                "matvec_frac_of_peak": (flops_local / (ms_step * 1e-3) / 1e12) / peak_tf if peak_tf else None}
+
+    # ---- e2e: ApplyMPO.forward with theta in pinned host memory, H2D + D2H inside the timed region
+    h_theta = torch.empty(n, dtype=dtype).pin_memory()
+    h_theta.copy_(theta.cpu())
+    h_out = torch.empty(n_loc, dtype=dtype).pin_memory()
+    d_theta = torch.empty_like(theta)
+
+    def step_e2e():
+        d_theta.copy_(h_theta, non_blocking=True)
+        op(d_theta, L, M1, M2, R, out=out)
+        h_out.copy_(out, non_blocking=True)
+
+    for _ in range(2):
+        step_e2e()
+    if world > 1:
+        dist.barrier()
+    Ke = max(3, min(K, 10))
+    sec_e = time_region(step_e2e, Ke)
+    if world > 1:
+        t = torch.tensor([sec_e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sec_e = float(t.item())
+    e2e = {"value": flops_total / (sec_e / Ke) / 1e9, "unit": UNIT, "h2d_bytes_per_step": n * es,
+           "d2h_bytes_per_step": n_loc * es, "ms_per_step": sec_e / Ke * 1e3, "steps": Ke,
+           "call": "quantum_simulation_b200.ApplyMPO.forward (torch.ops.qsb200.heff_apply -> qsb_heff_apply)"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic", "config": workload_config(args, world), "clocks": clocks,
+            "e2e": e2e, "gpu_launches": launches["total"], "launch_breakdown": launches, "roofline": roofline,
+            "tflops": value / 1e3, "frac_of_fp64_tensor_peak": (value / 1e3 / world) / peak_tf if peak_tf else None}
+
+    if rank == 0 and world == 1 and not args.no_extras:
+        line.update(extras(args, qsb, _lib, dev, dtype, L, M1, M2, R, theta, peak_tf))
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def extras(args, qsb, _lib, dev, dtype, L, M1, M2, R, theta, peak_tf):
+    """Library baselines on the same GPU, the other hot-path kernels, and the CPU baseline (rank 0, N = 1)."""
+    from oracle import dmrg_oracle as orc
+    out = {}
+    chi = args.chi
+    es = 8 if dtype == torch.float64 else 16
+    flops = _lib.heff_flops(theta, L, M1, M2, R)
+    # (1) cuBLAS DGEMM 8192^3 and the reference's ncon order executed by torch/cuBLAS on this GPU
+    try:
+        a = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
+        b = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
+        for _ in range(2):
+            torch.matmul(a, b)
+        s = time_region(lambda: torch.matmul(a, b), 5) / 5
+        out["cublas_dgemm_8192_tflops"] = 2 * 8192 ** 3 / s / 1e12
+        del a, b
+        for _ in range(2):
+            orc.apply_mpo(theta, L, M1, M2, R)
+        s = time_region(lambda: orc.apply_mpo(theta, L, M1, M2, R), 5) / 5
+        out["torch_cublas_same_matvec"] = {"gflops": flops / s / 1e9, "ms": s * 1e3,
+                                           "what": "oracle tensordot chain on device='cuda' (cuBLAS + permute copies)"}
+        torch.cuda.empty_cache()
+    except Exception as ex:          # library leg is informational only
+        out["library_leg_error"] = repr(ex)[:200]
+    # (2) Lanczos: one full solve (2 restarts x krylov 4 = 8 matvecs + fused vector ops), vector-op bandwidth
+    n = theta.numel()
+    op = qsb.ApplyMPO()
+    args_op = (L, M1, M2, R)
+    qsb.lanczos_ground_state(theta, op, args_op, num_restarts=2, krylov_dim=4)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    _, E = qsb.lanczos_ground_state(theta, op, args_op, num_restarts=2, krylov_dim=4)
+    torch.cuda.synchronize()
+    t_solve = time.perf_counter() - t0
+    ws = torch.empty(n, dtype=dtype, device=dev)
+    K2 = torch.randn(2, n, dtype=dtype, device=dev)
+    scal = torch.zeros(16, 2, dtype=torch.float64, device=dev)
+    scratch = torch.zeros(_lib.lz_scratch_bytes(), dtype=torch.uint8, device=dev)
+    ops = _lib.ops
+
+    def vec_iter():        # the vector ops of one Krylov iteration: dot, axpy2+norm, scale  (8 n-element passes)
+        ops.lz_dot(K2[1], 1, 0, ws, n, scal, 3, 1, scratch)
+        ops.lz_axpy_norm(K2, 2, n, ws, n, scal, 2, 4, scratch)
+        ops.lz_scale(ws, K2[0], n, scal, 5)
+    ws.copy_(theta)
+    scal[5, 0] = 1.0
+    for _ in range(3):
+        vec_iter()
+    s = time_region(vec_iter, 20) / 20
+    hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
+        os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    gbs = 8 * n * es / s / 1e9
+    out["lanczos"] = {"solve_ms": t_solve * 1e3, "matvecs": 8, "energy": E,
+                      "vector_ops_per_iteration_ms": s * 1e3, "algorithmic_bytes_per_iteration": 8 * n * es,
+                      "achieved_gbs": gbs, "hbm_peak_gbs": hbm, "frac_of_hbm_peak": gbs / hbm}
+    del ws, K2
+    # (3) environment update at the same bond
+    A = torch.randn(chi, M1.shape[2], chi, dtype=dtype, device=dev) / chi ** 0.5
+    up = qsb.LeftEnvUpdate()
+    Lsq = L if L.shape[1] == L.shape[2] else L[:, :, : L.shape[1]]
+    for _ in range(2):
+        up(Lsq, M1, A)
+    s = time_region(lambda: up(Lsq, M1, A), 5) / 5
+    ef = _lib.env_flops(Lsq, M1, A, True)
+    out["env_update"] = {"ms": s * 1e3, "gflops": ef / s / 1e9, "frac_of_fp64_tensor_peak": ef / s / 1e12 / peak_tf}
+    del A
+    torch.cuda.empty_cache()
+    # (4) CPU baseline: the oracle on the host cores, bounded sample of the same workload
+    cores = os.cpu_count() or 1
+    try:
+        rows = chi if chi <= 1024 else max(256, chi // 4)
+        ts, fl, threads = cpu_matvec_time(chi, dtype, 3, rows=rows)
+        sec = min(ts[1:])
+        out["cpu_baseline"] = {"value": fl / sec / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
+                               "sample": f"rows [0,{rows}) of {chi} of the same chi={chi} matvec, best of 2 after 1 "
+                                         f"warm-up, torch-CPU oracle (ncon order), {threads} threads",
+                               "ms_sample": sec * 1e3}
+    except Exception as ex:
+        out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": cores, "kind": "port", "sample": repr(ex)[:200]}
+    return out
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,419 @@
+"""ctypes binding of the qsb200 C ABI (include/qsb200.h) and its PyTorch custom-op registration.
+
+The shared library ``lib/libqsb200.so`` is built in-tree by ``build.py`` (nvcc, sm_100a).  There is no
+CPU fallback: if the library is missing, or a tensor is not on a CUDA device, the call raises.
+
+Every op is registered under ``torch.ops.qsb200`` with a CUDA-only implementation that unpacks
+``Tensor -> (data_ptr, strides, current stream)`` and calls the ``extern "C"`` entry point; status codes are
+mapped to the exception types the reference raises:
+
+  QSB_ERR_SHAPE                    -> AssertionError   (dmrg.py:233-237)
+  QSB_ERR_DTYPE / STRIDE / ARG     -> ValueError       (dmrg.py:224-225)
+  QSB_ERR_DEVICE / WORKSPACE / LAUNCH -> RuntimeError
+never TypeError (the reference's Lanczos swallows TypeError, lanczos_solver.py:236).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libqsb200.so")
+
+QSB_F64, QSB_C128, QSB_F32, QSB_C64 = 0, 1, 2, 3
+_DTYPE_CODE = {torch.float64: QSB_F64, torch.complex128: QSB_C128, torch.float32: QSB_F32, torch.complex64: QSB_C64}
+
+EXPORTS = [
+    "qsb_version", "qsb_status_string", "qsb_last_cuda_error", "qsb_launch_counters",
+    "qsb_heff_workspace_bytes", "qsb_heff_apply", "qsb_heff_flops", "qsb_heff_set_stage_events",
+    "qsb_env_workspace_bytes", "qsb_env_left", "qsb_env_right", "qsb_env_flops",
+    "qsb_lz_scratch_bytes", "qsb_lz_dot", "qsb_lz_axpy_norm", "qsb_lz_scale", "qsb_lz_combine",
+    "qsb_strided_copy3", "qsb_gemm", "qsb_probe_dmma",
+]
+
+
+class HeffDesc(C.Structure):
+    _fields_ = [
+        ("dtype", C.c_int),
+        ("chi_l_out", C.c_int), ("chi_l_in", C.c_int), ("chi_r_out", C.c_int), ("chi_r_in", C.c_int),
+        ("d1_out", C.c_int), ("d1_in", C.c_int), ("d2_out", C.c_int), ("d2_in", C.c_int),
+        ("W_l", C.c_int), ("W_m", C.c_int), ("W_r", C.c_int),
+        ("theta", C.c_void_p),
+        ("L", C.c_void_p), ("L_stride", C.c_int64 * 3),
+        ("M1", C.c_void_p), ("M2", C.c_void_p),
+        ("R", C.c_void_p), ("R_stride", C.c_int64 * 3),
+        ("out", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
+class EnvDesc(C.Structure):
+    _fields_ = [
+        ("dtype", C.c_int),
+        ("W_in", C.c_int), ("W_out", C.c_int), ("d", C.c_int), ("chi_in", C.c_int), ("chi_out", C.c_int),
+        ("env", C.c_void_p), ("env_stride", C.c_int64 * 3),
+        ("M", C.c_void_p),
+        ("site", C.c_void_p), ("site_stride", C.c_int64 * 3),
+        ("out", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [
+        ("dtype", C.c_int),
+        ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("P", C.c_int), ("Z", C.c_int),
+        ("A", C.c_void_p), ("a_ms", C.c_int64), ("a_ks", C.c_int64), ("a_ps", C.c_int64), ("a_zs", C.c_int64),
+        ("conjA", C.c_int),
+        ("B", C.c_void_p), ("b_ns", C.c_int64), ("b_ks", C.c_int64), ("b_ps", C.c_int64), ("b_zs", C.c_int64),
+        ("conjB", C.c_int),
+        ("C", C.c_void_p), ("c_ms", C.c_int64), ("c_ns", C.c_int64), ("c_zs", C.c_int64),
+        ("force_path", C.c_int),
+    ]
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def load() -> C.CDLL:
+    """Load libqsb200.so (once) and declare the prototypes.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"qsb200: CUDA library not found at {LIB_PATH}; build it with "
+            "`python -c 'import __graft_entry__ as g; g.build()'` (there is no CPU fallback).")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64 = C.c_void_p, C.c_int, C.c_int64
+    lib.qsb_version.restype = i32
+    lib.qsb_status_string.restype = C.c_char_p
+    lib.qsb_status_string.argtypes = [i32]
+    lib.qsb_last_cuda_error.restype = i32
+    lib.qsb_launch_counters.restype = None
+    lib.qsb_launch_counters.argtypes = [C.POINTER(C.c_uint64), i32]
+    lib.qsb_heff_workspace_bytes.argtypes = [C.POINTER(HeffDesc), C.POINTER(C.c_size_t)]
+    lib.qsb_heff_apply.argtypes = [C.POINTER(HeffDesc), vp]
+    lib.qsb_heff_flops.argtypes = [C.POINTER(HeffDesc)]
+    lib.qsb_heff_flops.restype = C.c_double
+    lib.qsb_heff_set_stage_events.argtypes = [C.POINTER(vp), i32]
+    lib.qsb_env_workspace_bytes.argtypes = [C.POINTER(EnvDesc), C.POINTER(C.c_size_t)]
+    lib.qsb_env_left.argtypes = [C.POINTER(EnvDesc), vp]
+    lib.qsb_env_right.argtypes = [C.POINTER(EnvDesc), vp]
+    lib.qsb_env_flops.argtypes = [C.POINTER(EnvDesc)]
+    lib.qsb_env_flops.restype = C.c_double
+    lib.qsb_lz_scratch_bytes.argtypes = [i32]
+    lib.qsb_lz_scratch_bytes.restype = C.c_size_t
+    lib.qsb_lz_dot.argtypes = [i32, i64, i32, vp, i64, vp, vp, i32, i32, vp, vp]
+    lib.qsb_lz_axpy_norm.argtypes = [i32, i64, i32, vp, i64, vp, vp, i32, i32, vp, vp]
+    lib.qsb_lz_scale.argtypes = [i32, i64, vp, vp, vp, i32, vp]
+    lib.qsb_lz_combine.argtypes = [i32, i64, i32, vp, i64, C.POINTER(C.c_double), vp, vp, i32, vp, vp]
+    lib.qsb_strided_copy3.argtypes = [i32, C.POINTER(i64), vp, C.POINTER(i64), vp, i32, vp]
+    lib.qsb_gemm.argtypes = [C.POINTER(GemmDesc), vp]
+    lib.qsb_probe_dmma.argtypes = [i32, C.POINTER(C.c_double), vp, vp]
+    for name in EXPORTS:          # every symbol include/qsb200.h declares must be exported
+        getattr(lib, name)
+    _lib = lib
+    return lib
+
+
+def status_string(code: int) -> str:
+    return load().qsb_status_string(int(code)).decode()
+
+
+def check(code: int, where: str) -> None:
+    """Map a qsb_status to the reference's exception types."""
+    if code == 0:
+        return
+    msg = f"[{where}] {status_string(code)} (qsb_status {code})"
+    if code == 1:
+        raise AssertionError(msg)
+    if code in (2, 3, 7):
+        raise ValueError(msg)
+    if code == 6:
+        msg += f"; cudaError {load().qsb_last_cuda_error()}"
+    raise RuntimeError(msg)
+
+
+def launch_counters(reset: bool = False) -> Dict[str, int]:
+    """Kernel launches issued by the library since load / last reset."""
+    out = (C.c_uint64 * 3)()
+    load().qsb_launch_counters(out, 1 if reset else 0)
+    return {"tma_gemm": int(out[0]), "cpasync_gemm": int(out[1]), "other": int(out[2]),
+            "total": int(out[0] + out[1] + out[2])}
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    try:
+        return _DTYPE_CODE[dt]
+    except KeyError:
+        raise ValueError(f"qsb200: unsupported dtype {dt}") from None
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(*tensors: torch.Tensor) -> torch.device:
+    dev = tensors[0].device
+    for t in tensors:
+        if t.device.type != "cuda":
+            raise RuntimeError("qsb200 kernels run on CUDA tensors only (no CPU fallback); got device "
+                               f"{t.device}")
+        if t.device != dev:
+            raise ValueError("qsb200: all tensors of one call must live on the same device")
+    return dev
+
+
+def _resolved(t: torch.Tensor) -> torch.Tensor:
+    """Materialise lazy conj/neg bits (torch.conj views) so data_ptr is the value the kernels read."""
+    if t.is_conj():
+        t = t.resolve_conj()
+    if t.is_neg():
+        t = t.resolve_neg()
+    return t
+
+
+# ---------------------------------------------------------------------------------------------
+# per-device workspaces (grown on demand, reused by every call on that device)
+# ---------------------------------------------------------------------------------------------
+_workspaces: Dict[torch.device, torch.Tensor] = {}
+
+
+def workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
+    ws = _workspaces.get(dev)
+    if ws is None or ws.numel() < nbytes:
+        _workspaces[dev] = None  # release before growing
+        ws = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=dev)
+        _workspaces[dev] = ws
+    return ws
+
+
+def release_workspaces() -> None:
+    _workspaces.clear()
+
+
+# ---------------------------------------------------------------------------------------------
+# descriptors
+# ---------------------------------------------------------------------------------------------
+def heff_desc(psi: torch.Tensor, L: torch.Tensor, M1: torch.Tensor, M2: torch.Tensor, R: torch.Tensor,
+              out: Optional[torch.Tensor]) -> HeffDesc:
+    if L.dim() != 3 or R.dim() != 3 or M1.dim() != 4 or M2.dim() != 4:
+        raise AssertionError("[ApplyMPO] expected L,R rank 3 and M1,M2 rank 4")
+    d = HeffDesc()
+    d.dtype = dtype_code(psi.dtype)
+    d.W_l, d.chi_l_out, d.chi_l_in = L.shape
+    Wl1, d.W_m, d.d1_out, d.d1_in = M1.shape
+    Wm2, d.W_r, d.d2_out, d.d2_in = M2.shape
+    Wr3, d.chi_r_out, d.chi_r_in = R.shape
+    # the reference's einsum branch asserts exactly these (dmrg.py:233-237)
+    assert Wl1 == d.W_l, "Mismatch in left MPO bond dimension"
+    assert Wm2 == d.W_m, "Mismatch in middle MPO bond dimension"
+    assert Wr3 == d.W_r, "Mismatch in right MPO bond dimension"
+    d.theta = psi.data_ptr()
+    d.L = L.data_ptr()
+    d.L_stride = (C.c_int64 * 3)(*L.stride())
+    d.M1 = M1.data_ptr()
+    d.M2 = M2.data_ptr()
+    d.R = R.data_ptr()
+    d.R_stride = (C.c_int64 * 3)(*R.stride())
+    d.out = out.data_ptr() if out is not None else None
+    return d
+
+
+def heff_flops(psi, L, M1, M2, R) -> float:
+    return float(load().qsb_heff_flops(C.byref(heff_desc(psi, L, M1, M2, R, None))))
+
+
+def _impl_heff_apply(psi, L, M1, M2, R, out) -> None:
+    lib = load()
+    dev = _require_cuda(psi, L, M1, M2, R, out)
+    d = heff_desc(psi, L, M1, M2, R, out)
+    nb = C.c_size_t(0)
+    check(lib.qsb_heff_workspace_bytes(C.byref(d), C.byref(nb)), "ApplyMPO")
+    ws = workspace(dev, nb.value)
+    d.workspace = ws.data_ptr()
+    d.workspace_bytes = ws.numel()
+    with torch.cuda.device(dev):
+        check(lib.qsb_heff_apply(C.byref(d), _stream()), "ApplyMPO")
+
+
+def env_desc(env: torch.Tensor, M: torch.Tensor, site: torch.Tensor, out: Optional[torch.Tensor],
+             left: bool) -> EnvDesc:
+    if env.dim() != 3 or M.dim() != 4 or site.dim() != 3:
+        raise AssertionError("[EnvUpdate] expected env rank 3, M rank 4, site tensor rank 3")
+    d = EnvDesc()
+    d.dtype = dtype_code(env.dtype)
+    W_in, chi_a, chi_b = env.shape
+    assert chi_a == chi_b, "environment must be square in its two MPS bonds"
+    if left:
+        Wi, Wo, d1, d2 = M.shape
+        ci, ds, co = site.shape
+    else:
+        Wo, Wi, d1, d2 = M.shape
+        co, ds, ci = site.shape
+    assert Wi == W_in, "Mismatch between environment and MPO bond dimension"
+    assert d1 == d2 == ds, "Mismatch in physical dimension"
+    assert ci == chi_a, "Mismatch between environment and MPS bond dimension"
+    d.W_in, d.W_out, d.d, d.chi_in, d.chi_out = W_in, Wo, ds, ci, co
+    d.env = env.data_ptr()
+    d.env_stride = (C.c_int64 * 3)(*env.stride())
+    d.M = M.data_ptr()
+    d.site = site.data_ptr()
+    d.site_stride = (C.c_int64 * 3)(*site.stride())
+    d.out = out.data_ptr() if out is not None else None
+    return d
+
+
+def env_flops(env, M, site, left: bool) -> float:
+    return float(load().qsb_env_flops(C.byref(env_desc(env, M, site, None, left))))
+
+
+def _impl_env(env, M, site, out, left: bool) -> None:
+    lib = load()
+    dev = _require_cuda(env, M, site, out)
+    d = env_desc(env, M, site, out, left)
+    nb = C.c_size_t(0)
+    check(lib.qsb_env_workspace_bytes(C.byref(d), C.byref(nb)), "EnvUpdate")
+    ws = workspace(dev, nb.value)
+    d.workspace = ws.data_ptr()
+    d.workspace_bytes = ws.numel()
+    with torch.cuda.device(dev):
+        check((lib.qsb_env_left if left else lib.qsb_env_right)(C.byref(d), _stream()),
+              "LeftEnvUpdate" if left else "RightEnvUpdate")
+
+
+def _impl_env_left(env, M, site, out) -> None:
+    _impl_env(env, M, site, out, True)
+
+
+def _impl_env_right(env, M, site, out) -> None:
+    _impl_env(env, M, site, out, False)
+
+
+def _impl_lz_dot(X, m: int, ldx: int, w, n: int, scal, out_idx: int, flags: int, scratch) -> None:
+    dev = _require_cuda(X, w, scal, scratch)
+    with torch.cuda.device(dev):
+        check(load().qsb_lz_dot(dtype_code(w.dtype), n, m, X.data_ptr(), ldx, w.data_ptr(), scal.data_ptr(),
+                                out_idx, flags, scratch.data_ptr(), _stream()), "lanczos.dot")
+
+
+def _impl_lz_axpy_norm(X, m: int, ldx: int, w, n: int, scal, coef_idx: int, norm_idx: int, scratch) -> None:
+    dev = _require_cuda(X, w, scal, scratch)
+    with torch.cuda.device(dev):
+        check(load().qsb_lz_axpy_norm(dtype_code(w.dtype), n, m, X.data_ptr(), ldx, w.data_ptr(),
+                                      scal.data_ptr(), coef_idx, norm_idx, scratch.data_ptr(), _stream()),
+              "lanczos.axpy_norm")
+
+
+def _impl_lz_scale(src, dst, n: int, scal, idx: int) -> None:
+    dev = _require_cuda(src, dst, scal)
+    with torch.cuda.device(dev):
+        check(load().qsb_lz_scale(dtype_code(src.dtype), n, src.data_ptr(), dst.data_ptr(), scal.data_ptr(), idx,
+                                  _stream()), "lanczos.scale")
+
+
+def _impl_lz_combine(X, m: int, ldx: int, y: Sequence[float], dst, n: int, scal, norm_idx: int, scratch) -> None:
+    dev = _require_cuda(X, dst, scal, scratch)
+    yy = (C.c_double * len(y))(*[float(v) for v in y])
+    with torch.cuda.device(dev):
+        check(load().qsb_lz_combine(dtype_code(dst.dtype), n, m, X.data_ptr(), ldx, yy, dst.data_ptr(),
+                                    scal.data_ptr(), norm_idx, scratch.data_ptr(), _stream()), "lanczos.combine")
+
+
+def set_stage_events(events: Optional[Sequence[torch.cuda.Event]]) -> None:
+    """Profiling hook of qsb_heff_apply: four recorded-once torch events, or None to clear."""
+    lib = load()
+    if not events:
+        check(lib.qsb_heff_set_stage_events(None, 0), "set_stage_events")
+        return
+    arr = (C.c_void_p * 4)(*[C.c_void_p(e.cuda_event) for e in events])
+    check(lib.qsb_heff_set_stage_events(arr, 4), "set_stage_events")
+
+
+def lz_scratch_bytes() -> int:
+    return int(load().qsb_lz_scratch_bytes(64))
+
+
+# ---------------------------------------------------------------------------------------------
+# plain GEMM (tests, peak probe)
+# ---------------------------------------------------------------------------------------------
+def gemm(A: torch.Tensor, B: torch.Tensor, *, conjA: bool = False, conjB: bool = False,
+         force_path: int = 0) -> torch.Tensor:
+    """C[z] = opA(A[z]) @ opB(B[z]) on the library's FP64 tensor-core core.  A: (Z, M, K) or (M, K);
+    B: (Z, K, N) or (K, N); any strides with one unit stride per matrix."""
+    lib = load()
+    dev = _require_cuda(A, B)
+    squeeze = A.dim() == 2
+    if squeeze:
+        A, B = A.unsqueeze(0), B.unsqueeze(0)
+    Z, M, K = A.shape
+    Zb, Kb, N = B.shape
+    assert Kb == K and Zb in (1, Z)
+    out = torch.empty(Z, M, N, dtype=A.dtype, device=dev)
+    g = GemmDesc()
+    g.dtype = dtype_code(A.dtype)
+    g.M, g.N, g.K, g.P, g.Z = M, N, K, 1, Z
+    g.A, g.a_zs, g.a_ms, g.a_ks, g.a_ps, g.conjA = A.data_ptr(), A.stride(0), A.stride(1), A.stride(2), 0, int(conjA)
+    g.B, g.b_zs, g.b_ks, g.b_ns, g.b_ps, g.conjB = (B.data_ptr(), B.stride(0) if Zb == Z else 0, B.stride(1),
+                                                   B.stride(2), 0, int(conjB))
+    g.C, g.c_zs, g.c_ms, g.c_ns = out.data_ptr(), M * N, N, 1
+    g.force_path = force_path
+    with torch.cuda.device(dev):
+        check(lib.qsb_gemm(C.byref(g), _stream()), "gemm")
+    return out[0] if squeeze else out
+
+
+def probe_dmma_tflops(iters: int = 20000, reps: int = 3) -> float:
+    """Register-resident DMMA issue rate of this GPU in TFLOP/s (the FP64 tensor-pipe peak)."""
+    lib = load()
+    sink = torch.zeros(8, dtype=torch.float64, device="cuda")
+    flops = C.c_double(0.0)
+    best = 0.0
+    for r in range(reps + 1):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(lib.qsb_probe_dmma(iters, C.byref(flops), sink.data_ptr(), _stream()), "probe_dmma")
+        e1.record()
+        e1.synchronize()
+        if r > 0:
+            best = max(best, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    return best
+
+
+# ---------------------------------------------------------------------------------------------
+# torch custom-op registration (CUDA only)
+# ---------------------------------------------------------------------------------------------
+_torch_lib: Optional[torch.library.Library] = None
+
+
+def register_ops() -> None:
+    global _torch_lib
+    if _torch_lib is not None:
+        return
+    tl = torch.library.Library("qsb200", "DEF")
+    tl.define("heff_apply(Tensor psi, Tensor L, Tensor M1, Tensor M2, Tensor R, Tensor(a!) out) -> ()")
+    tl.define("env_left(Tensor env, Tensor M, Tensor site, Tensor(a!) out) -> ()")
+    tl.define("env_right(Tensor env, Tensor M, Tensor site, Tensor(a!) out) -> ()")
+    tl.define("lz_dot(Tensor X, int m, int ldx, Tensor w, int n, Tensor(a!) scal, int out_idx, int flags, "
+              "Tensor(b!) scratch) -> ()")
+    tl.define("lz_axpy_norm(Tensor X, int m, int ldx, Tensor(a!) w, int n, Tensor(b!) scal, int coef_idx, "
+              "int norm_idx, Tensor(c!) scratch) -> ()")
+    tl.define("lz_scale(Tensor src, Tensor(a!) dst, int n, Tensor scal, int idx) -> ()")
+    tl.define("lz_combine(Tensor X, int m, int ldx, float[] y, Tensor(a!) dst, int n, Tensor(b!) scal, "
+              "int norm_idx, Tensor(c!) scratch) -> ()")
+    tl.impl("heff_apply", _impl_heff_apply, "CUDA")
+    tl.impl("env_left", _impl_env_left, "CUDA")
+    tl.impl("env_right", _impl_env_right, "CUDA")
+    tl.impl("lz_dot", _impl_lz_dot, "CUDA")
+    tl.impl("lz_axpy_norm", _impl_lz_axpy_norm, "CUDA")
+    tl.impl("lz_scale", _impl_lz_scale, "CUDA")
+    tl.impl("lz_combine", _impl_lz_combine, "CUDA")
+    _torch_lib = tl
+
+
+register_ops()
+ops = torch.ops.qsb200

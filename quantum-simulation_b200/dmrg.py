@@ -1,0 +1,358 @@
+"""Two-site DMRG on the sm_100a kernels: host-side mirror of ``quantum_simulation/dmrg.py``.
+
+Same public names, arguments and error behaviour as the reference (file:line relative to
+/root/reference/quantum_simulation/):
+
+  ApplyMPO            dmrg.py:165-248     H_eff . theta              -> torch.ops.qsb200.heff_apply
+  LeftEnvUpdate       dmrg.py:251-278     L[p+1] from L[p], M[p], A  -> torch.ops.qsb200.env_left
+  RightEnvUpdate      dmrg.py:281-308     R[p]   from M[p], R[p+1], B-> torch.ops.qsb200.env_right
+  EnvironmentManager  dmrg.py:311-418
+  Sweeps              dmrg.py:424-503
+  DMRG                dmrg.py:506-802
+  set_contract_backend dmrg.py:85-107
+
+The ``contract_backend`` names ``'auto' | 'einsum' | 'ncon'`` are accepted so notebooks run unchanged, but all
+three route to the same CUDA kernels -- there is no multi-backend dispatch and no CPU fallback.  Results follow
+the reference's ncon path (the optimal contraction order) to ~1e-15 relative.
+
+Environment layout: the reference's ncon branch returns environments as a permuted view with strides
+``(chi, 1, W*chi)``; ours are contiguous ``(W, chi, chi)`` -- the kernels take either.
+"""
+from __future__ import annotations
+
+from typing import Any, List, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .eigensolver import lanczos_ground_state
+from .mps import MPS
+
+__all__ = ["ApplyMPO", "LeftEnvUpdate", "RightEnvUpdate", "EnvironmentManager", "Sweeps", "DMRG",
+           "set_contract_backend"]
+
+_BACKENDS = ("auto", "einsum", "ncon")
+_CONTRACT_BACKEND = "qsb200"
+
+
+def set_contract_backend(backend: str = "auto", device: Any = "cpu") -> None:
+    """Validates the reference's backend name (dmrg.py:85-107).  Every valid name resolves to the CUDA kernels."""
+    dev = device if isinstance(device, str) else getattr(device, "type", "cpu")
+    if backend not in _BACKENDS:
+        raise ValueError(f"Unknown backend: {backend!r} (valid: 'auto'|'einsum'|'ncon')")
+    print(f"[DMRG] Contraction backend resolved to 'qsb200-cuda' (requested '{backend}') on device='{dev}'.")
+
+
+def _as_mpo_list(M_or_Ms: Any, Nsites: int, device: Any, dtype: torch.dtype) -> List[torch.Tensor]:
+    """dmrg.py:17-43 (numpy site tensors are accepted here; the reference's numpy branch cannot run)."""
+    def conv(m):
+        if isinstance(m, np.ndarray):
+            m = torch.from_numpy(np.ascontiguousarray(m))
+        if m.is_complex() and not dtype.is_complex:
+            if float(m.imag.abs().max()) != 0.0:
+                raise ValueError("MPO has a non-zero imaginary part but a real dtype was requested "
+                                 "(the reference silently drops it, giving the wrong Hamiltonian)")
+            m = m.real
+        return m.to(device=device, dtype=dtype).contiguous()
+    if isinstance(M_or_Ms, (list, tuple)):
+        assert len(M_or_Ms) == Nsites, f"MPO list length {len(M_or_Ms)} != Nsites {Nsites}"
+        return [conv(m) for m in M_or_Ms]
+    return [conv(M_or_Ms) for _ in range(Nsites)]
+
+
+def _check_mpo_shapes(Ms: List[torch.Tensor], ML: torch.Tensor, MR: torch.Tensor, chid: int) -> None:
+    """dmrg.py:46-77."""
+    for p, M in enumerate(Ms):
+        assert M.ndim == 4, f"Ms[{p}] must be rank-4 (Wl,Wr,d,d), got {tuple(M.shape)}"
+        assert M.shape[2] == chid and M.shape[3] == chid, \
+            f"Ms[{p}] physical dims {tuple(M.shape[2:])} != (d,d)=({chid},{chid})"
+        if p < len(Ms) - 1:
+            assert M.shape[1] == Ms[p + 1].shape[0], \
+                f"MPO bond mismatch: Ms[{p}].Wr={M.shape[1]} != Ms[{p + 1}].Wl={Ms[p + 1].shape[0]}"
+    assert ML.shape[0] == Ms[0].shape[0], f"ML W={ML.shape[0]} must match Ms[0].Wl={Ms[0].shape[0]}"
+    assert MR.shape[0] == Ms[-1].shape[1], f"MR W={MR.shape[0]} must match Ms[-1].Wr={Ms[-1].shape[1]}"
+
+
+class _BaseContractModule(nn.Module):
+    """dmrg.py:127-162: validates and stores the backend policy."""
+
+    def __init__(self, contract_backend: str = "auto"):
+        super().__init__()
+        if contract_backend not in _BACKENDS:
+            raise ValueError("contract backend must be 'auto'|'einsum'|'ncon'")
+        self.contract_backend = contract_backend
+
+    def _resolved(self, ref: torch.Tensor) -> str:
+        return _CONTRACT_BACKEND
+
+
+def _dev_tensor(t: torch.Tensor) -> torch.Tensor:
+    return _lib._resolved(t.detach() if t.requires_grad else t)
+
+
+class ApplyMPO(_BaseContractModule):
+    r"""H_eff . theta = L . M1 . M2 . R . theta for the two-site block (dmrg.py:165-248).
+
+    ``psi_flat`` is the row-major flattening of theta[a, s1, s2, b]; ``L[w, a', a]``, ``M[w_l, w_r, s', s]``,
+    ``R[w, b', b]`` (dmrg.py:188-207).  L and R may have any strides.
+    """
+
+    def forward(self, psi_flat: torch.Tensor, L: torch.Tensor, M1: torch.Tensor, M2: torch.Tensor,
+                R: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        psi, L, M1, M2, R = (_dev_tensor(t) for t in (psi_flat, L, M1, M2, R))
+        if not psi.is_contiguous():
+            psi = psi.contiguous()
+        if not M1.is_contiguous():
+            M1 = M1.contiguous()
+        if not M2.is_contiguous():
+            M2 = M2.contiguous()
+        n_in = L.shape[2] * M1.shape[3] * M2.shape[3] * R.shape[2]
+        if psi.numel() != n_in:
+            raise AssertionError(f"[ApplyMPO] psi has {psi.numel()} elements, the operator expects {n_in}")
+        n_out = L.shape[1] * M1.shape[2] * M2.shape[2] * R.shape[1]
+        if out is not None:
+            if out.numel() != n_out or out.device != psi.device or out.dtype != psi.dtype \
+                    or not out.is_contiguous():
+                raise ValueError("[ApplyMPO] out shape/device/dtype mismatch.")      # dmrg.py:224-225
+            res = out.view(-1)
+        else:
+            res = torch.empty(n_out, device=psi.device, dtype=psi.dtype)
+        _lib.ops.heff_apply(psi.view(-1), L, M1, M2, R, res)
+        return res
+
+
+class LeftEnvUpdate(_BaseContractModule):
+    """L[p+1][w', c'_bra, c_ket] = sum L[p] . conj(A) . M . A  (dmrg.py:251-278); returns contiguous (W', chi', chi')."""
+
+    def forward(self, Lp: torch.Tensor, M: torch.Tensor, Ap: torch.Tensor) -> torch.Tensor:
+        Lp, M, Ap = (_dev_tensor(t) for t in (Lp, M, Ap))
+        if not M.is_contiguous():
+            M = M.contiguous()
+        out = torch.empty(M.shape[1], Ap.shape[2], Ap.shape[2], device=Lp.device, dtype=Lp.dtype)
+        _lib.ops.env_left(Lp, M, Ap, out)
+        return out
+
+
+class RightEnvUpdate(_BaseContractModule):
+    """R[p][w, a'_bra, a_ket] = sum M . R[p+1] . B . conj(B)  (dmrg.py:281-308); returns contiguous (W, chi, chi)."""
+
+    def forward(self, M: torch.Tensor, Rnext: torch.Tensor, Bp1: torch.Tensor) -> torch.Tensor:
+        M, Rnext, Bp1 = (_dev_tensor(t) for t in (M, Rnext, Bp1))
+        if not M.is_contiguous():
+            M = M.contiguous()
+        out = torch.empty(M.shape[0], Bp1.shape[0], Bp1.shape[0], device=Rnext.device, dtype=Rnext.dtype)
+        _lib.ops.env_right(Rnext, M, Bp1, out)
+        return out
+
+
+class EnvironmentManager:
+    """Caches L[0..N] and R[0..N]; boundaries are ones(W,1,1)  (dmrg.py:311-418)."""
+
+    def __init__(self, mpo: List[torch.Tensor], device: Any, dtype: torch.dtype, contract_backend: str = "auto"):
+        self.mpo = mpo
+        self.Nsites = len(mpo)
+        self.device = device
+        self.dtype = dtype
+        self.L_cache: List[Optional[torch.Tensor]] = [None] * (self.Nsites + 1)
+        self.R_cache: List[Optional[torch.Tensor]] = [None] * (self.Nsites + 1)
+        self.L_cache[0] = torch.ones(self.mpo[0].shape[0], 1, 1, device=device, dtype=dtype)
+        self.R_cache[self.Nsites] = torch.ones(self.mpo[self.Nsites - 1].shape[1], 1, 1, device=device, dtype=dtype)
+        self._left_upd = LeftEnvUpdate(contract_backend)
+        self._right_upd = RightEnvUpdate(contract_backend)
+
+    def get_L(self, site_idx: int) -> torch.Tensor:
+        if self.L_cache[site_idx] is None:
+            raise RuntimeError(f"L[{site_idx}] requested but not yet computed.")
+        return self.L_cache[site_idx]
+
+    def get_R(self, site_idx: int) -> torch.Tensor:
+        if self.R_cache[site_idx] is None:
+            raise RuntimeError(f"R[{site_idx}] requested but not yet computed.")
+        return self.R_cache[site_idx]
+
+    def update_L(self, site_idx: int, A_tensor: torch.Tensor) -> None:
+        self.L_cache[site_idx + 1] = self._left_upd(self.get_L(site_idx), self.mpo[site_idx], A_tensor)
+
+    def update_R(self, site_idx: int, B_tensor: torch.Tensor) -> None:
+        self.R_cache[site_idx] = self._right_upd(self.mpo[site_idx], self.get_R(site_idx + 1), B_tensor)
+
+
+class Sweeps:
+    """Per-sweep schedule (dmrg.py:424-503)."""
+
+    def __init__(self, numsweeps: int):
+        if numsweeps <= 0:
+            raise ValueError("Number of sweeps must be positive.")
+        self.numsweeps = numsweeps
+        self.maxdim = [10] * numsweeps
+        self.noise = [0.0] * numsweeps
+        self.krylov_dim = [4] * numsweeps
+        self.cutoff = [1e-12] * numsweeps
+        self.reortho = [False] * numsweeps
+        self.maxreortho = [1] * numsweeps
+
+    def set_schedule(self, **kwargs) -> None:
+        for key, val in kwargs.items():
+            if not hasattr(self, key):
+                raise AttributeError(f"Sweeps object does not have parameter '{key}'")
+            if len(val) != self.numsweeps:
+                raise ValueError(f"Length of schedule for '{key}' ({len(val)}) "
+                                 f"does not match the number of sweeps ({self.numsweeps})")
+            setattr(self, key, val)
+
+    def __repr__(self) -> str:
+        rows = [f"Sweeps({self.numsweeps}):"]
+        for name in ("maxdim", "noise", "krylov_dim", "cutoff", "reortho", "maxreortho"):
+            rows.append(f"  {name}: {getattr(self, name)}")
+        return "\n".join(rows) + "\n"
+
+
+class DMRG(nn.Module):
+    """Two-site DMRG driver (dmrg.py:506-802): same constructor, ``forward`` and ``history`` keys."""
+
+    def __init__(self, mps: MPS, mpo: Any, *, device: Any = "cuda", dtype: torch.dtype = torch.float64,
+                 contract_backend: str = "auto"):
+        super().__init__()
+        set_contract_backend(contract_backend, device)
+        if torch.device(device).type != "cuda":
+            raise RuntimeError("qsb200 DMRG runs on a CUDA device only (no CPU fallback); got device="
+                               f"{device!r}")
+        self.device = device
+        self.dtype = dtype
+        self.contract_backend = contract_backend
+        self.mps = mps
+        self.Nsites = len(mpo)
+        self.Ms = _as_mpo_list(list(mpo), self.Nsites, device, dtype)
+        self.ML = torch.ones(self.Ms[0].shape[0], 1, 1, device=device, dtype=dtype)
+        self.MR = torch.ones(self.Ms[-1].shape[1], 1, 1, device=device, dtype=dtype)
+        self.chid = self.Ms[0].shape[2]
+        _check_mpo_shapes(self.Ms, self.ML, self.MR, self.chid)
+        self.apply_mpo = ApplyMPO(contract_backend)
+        self.history = self._empty_history()
+
+    @staticmethod
+    def _empty_history() -> dict:
+        return {"energies": [], "discarded_weights": [], "bond_dims": [], "sweeps": [], "directions": [],
+                "sites": []}
+
+    # -- one half sweep (dmrg.py:577-722) ---------------------------------------------------------
+    def _sweep(self, direction: str, mps: MPS, env_manager: EnvironmentManager, sweep_params: dict,
+               Ekeep: List[float]) -> List[float]:
+        chi, noise, krydim = sweep_params["chi"], sweep_params["noise"], sweep_params["krydim"]
+        cutoff, dispon, updateon = sweep_params["cutoff"], sweep_params["dispon"], sweep_params["updateon"]
+        maxit, reortho, maxreortho = sweep_params["maxit"], sweep_params["reortho"], sweep_params["maxreortho"]
+        sweep_idx, numsweeps = sweep_params["sweep_idx"], sweep_params["numsweeps"]
+        A, B, sWeight = mps.A, mps.B, mps.sWeight
+        d = self.chid
+        sites = range(self.Nsites - 1) if direction == "right" else range(self.Nsites - 2, -1, -1)
+        for p in sites:
+            # 1. two-site wavefunction (dmrg.py:633-662)
+            if direction == "right":
+                left_t, right_t = B[p], B[p + 1]
+                sw = sWeight[p]
+                if sw.dim() == 2:
+                    sw = torch.diagonal(sw, 0)
+                l, s, m = left_t.shape
+                _m, t, r = right_t.shape
+                psi = torch.matmul(torch.mul(left_t, sw.to(left_t.dtype).view(-1, 1, 1)).reshape(l * s, m),
+                                   right_t.reshape(m, t * r))
+            else:
+                left_t, right_t = A[p], A[p + 1]
+                sw = sWeight[p + 2]
+                if sw.dim() == 2:
+                    sw = torch.diagonal(sw, 0)
+                l, s, m = left_t.shape
+                _m, t, r = right_t.shape
+                psi = torch.matmul(left_t.reshape(l * s, m),
+                                   torch.mul(right_t, sw.to(right_t.dtype).view(1, 1, -1)).reshape(m, t * r))
+            chil, chir = l, r
+            psi_flat = psi.reshape(-1)
+
+            # 2. Lanczos ground state of H_eff (dmrg.py:664-675)
+            if updateon:
+                operator_args = (env_manager.get_L(p), self.Ms[p], self.Ms[p + 1], env_manager.get_R(p + 2))
+                psi_flat, Entemp = lanczos_ground_state(
+                    psi_flat, self.apply_mpo, operator_args, num_restarts=maxit, krylov_dim=krydim,
+                    pro=reortho, pro_max_reorth=maxreortho)
+                Ekeep.append(Entemp)
+                self.history["energies"].append(float(Entemp))
+
+            # 3. optional noise, global RNG, uniform [0,1) like the reference (dmrg.py:677-682)
+            if noise > 0:
+                noise_vec = torch.rand_like(psi_flat)
+                noise_vec.div_(torch.linalg.norm(noise_vec))
+                psi_flat = psi_flat + noise_vec * noise
+                psi_flat.div_(torch.linalg.norm(psi_flat))
+
+            # 4. SVD + truncation + MPS update (dmrg.py:684-711)
+            U, S, Vh = torch.linalg.svd(psi_flat.view(chil * d, d * chir), full_matrices=False)
+            keep_max = min(S.numel(), chi)
+            keep_cut = S.numel()
+            if cutoff > 0.0:
+                S2 = S ** 2
+                csum = torch.cumsum(S2 / torch.sum(S2), dim=0)
+                keep_cut = int(torch.searchsorted(csum, 1.0 - cutoff, right=True)) + 1
+            keep = max(1, min(keep_max, keep_cut))
+            self.history["discarded_weights"].append(torch.sum(S[keep:] ** 2).real.item())
+            self.history["bond_dims"].append(int(keep))
+            self.history["sweeps"].append(int(sweep_idx))
+            self.history["directions"].append(direction)
+            self.history["sites"].append(int(p))
+            sv = S[:keep]
+            denom = sv.norm().add_(torch.finfo(sv.dtype).eps)
+            A[p] = nn.Parameter(U[:, :keep].view(chil, d, keep), requires_grad=False)
+            sWeight[p + 1] = nn.Parameter(sv.div(denom), requires_grad=False)
+            B[p + 1] = nn.Parameter(Vh[:keep, :].view(keep, d, chir), requires_grad=False)
+
+            # 5. environment update (dmrg.py:713-717)
+            if direction == "right":
+                env_manager.update_L(p, A[p])
+            else:
+                env_manager.update_R(p + 1, B[p + 1])
+            if dispon == 2 and updateon:
+                print(f"Sweep: {sweep_idx} of {numsweeps}, Loc: {p}, Energy: {Ekeep[-1]:.6f}")
+        return Ekeep
+
+    # -- full schedule (dmrg.py:725-802) -----------------------------------------------------------
+    def forward(self, sweeps: Sweeps, *, dispon=2, updateon=True, maxit=2):
+        Ekeep: List[float] = []
+        self.history = self._empty_history()
+        N, d = self.Nsites, self.chid
+        env_manager = EnvironmentManager(self.Ms, self.device, self.dtype, self.contract_backend)
+        for p in range(N - 1, self.mps.ortho_center, -1):
+            env_manager.update_R(p, self.mps.B[p])
+        for k in range(1, sweeps.numsweeps + 1):
+            params = {"chi": sweeps.maxdim[k - 1], "noise": sweeps.noise[k - 1], "krydim": sweeps.krylov_dim[k - 1],
+                      "cutoff": sweeps.cutoff[k - 1], "reortho": sweeps.reortho[k - 1],
+                      "maxreortho": sweeps.maxreortho[k - 1], "dispon": dispon, "updateon": updateon,
+                      "maxit": maxit, "sweep_idx": k, "numsweeps": sweeps.numsweeps}
+            Ekeep = self._sweep("right", self.mps, env_manager, params, Ekeep)
+            self.mps.ortho_center = N - 1
+            sw = self.mps.sWeight[N - 1]                                    # right boundary (dmrg.py:769-781)
+            if sw.dim() == 2:
+                sw = torch.diagonal(sw, 0)
+            B_last = self.mps.B[N - 1]
+            Atemp = (sw.to(B_last.dtype).view(-1, 1, 1) * B_last).reshape(B_last.shape[0] * d, B_last.shape[2])
+            U, S, Vh = torch.linalg.svd(Atemp, full_matrices=False)
+            eps = torch.finfo(S.dtype).eps
+            self.mps.A[N - 1] = nn.Parameter(U.view(B_last.shape[0], d, B_last.shape[2]), requires_grad=False)
+            self.mps.sWeight[N] = nn.Parameter((S.unsqueeze(1) * Vh).to(self.dtype) / (S.norm().add_(eps)),
+                                               requires_grad=False)
+            Ekeep = self._sweep("left", self.mps, env_manager, params, Ekeep)
+            self.mps.ortho_center = 0
+            sw = self.mps.sWeight[1]                                        # left boundary (dmrg.py:787-796)
+            if sw.dim() == 2:
+                sw = torch.diagonal(sw, 0)
+            A0 = self.mps.A[0] * sw.to(self.mps.A[0].dtype).view(1, 1, -1)
+            chil, _, chir = self.mps.A[0].shape
+            U, S, Vh = torch.linalg.svd(A0.reshape(chil, d * chir), full_matrices=False)
+            self.mps.B[0] = nn.Parameter(Vh.view(chil, d, chir), requires_grad=False)
+            self.mps.sWeight[0] = nn.Parameter((U * S.unsqueeze(0)).to(self.dtype) / (S.norm().add_(eps)),
+                                               requires_grad=False)
+            if dispon == 1:
+                print(f"Sweep: {k} of {sweeps.numsweeps}, Energy: {Ekeep[-1]:.12f}, "
+                      f"Bond dim: {self.mps.A[N // 2].shape[-1]}, Noise: {sweeps.noise[k - 1]:.2e}, "
+                      f"Cutoff: {sweeps.cutoff[k - 1]:.2e}")
+        return Ekeep, self.mps

@@ -1,0 +1,124 @@
+"""CPU-side checks: the C-ABI library builds/loads and exports every symbol include/qsb200.h declares; the
+host-side mirror has the reference's API surface and error behaviour; nothing computes without a GPU."""
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT
+import quantum_simulation_b200 as qsb
+from quantum_simulation_b200 import _lib
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "qsb200.h")).read()
+    declared = sorted(set(re.findall(r"^\s*(?:int|double|size_t|void|const char\*)\s+(qsb_[a-z0-9_]+)\s*\(", hdr, re.M)))
+    assert len(declared) >= 19
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in qsb200.h but not exported"
+    assert sorted(_lib.EXPORTS) == declared
+    assert lib.qsb_version() >= 100
+    assert _lib.status_string(0) == "ok" and "workspace" in _lib.status_string(5)
+    c = qsb.launch_counters(reset=True)
+    assert c["total"] == 0
+
+
+def test_descriptor_validation_without_gpu():
+    lib = _lib.load()
+    import ctypes as C
+    d = _lib.HeffDesc()
+    d.dtype = 0
+    nb = C.c_size_t(0)
+    assert lib.qsb_heff_workspace_bytes(C.byref(d), C.byref(nb)) == 1          # zero extents -> QSB_ERR_SHAPE
+    for f in ("chi_l_out", "chi_l_in", "chi_r_out", "chi_r_in"):
+        setattr(d, f, 64)
+    for f in ("d1_out", "d1_in", "d2_out", "d2_in"):
+        setattr(d, f, 2)
+    d.W_l = d.W_m = d.W_r = 5
+    d.L_stride = (C.c_int64 * 3)(64 * 64, 64, 1)
+    d.R_stride = (C.c_int64 * 3)(64 * 64, 64, 1)
+    assert lib.qsb_heff_workspace_bytes(C.byref(d), C.byref(nb)) == 0
+    assert nb.value >= 2 * 5 * 4 * 64 * 64 * 8
+    flops = lib.qsb_heff_flops(C.byref(d))
+    assert flops == 2.0 * (2 * 5 * 64 ** 3 * 4 + 2 * 10 * 10 * 2 * 64 * 64)
+    d.dtype = 7
+    assert lib.qsb_heff_workspace_bytes(C.byref(d), C.byref(nb)) == 2          # QSB_ERR_DTYPE
+    assert lib.qsb_heff_apply(C.byref(d), None) == 2
+    e = _lib.EnvDesc()
+    assert lib.qsb_env_workspace_bytes(C.byref(e), C.byref(nb)) == 1
+
+
+def test_api_surface_matches_reference():
+    for name in ("ApplyMPO", "LeftEnvUpdate", "RightEnvUpdate", "EnvironmentManager", "Sweeps", "DMRG", "MPS",
+                 "lanczos_ground_state", "set_contract_backend", "random_mps"):
+        assert hasattr(qsb, name)
+    import inspect
+    sig = inspect.signature(qsb.lanczos_ground_state)
+    assert list(sig.parameters) == ["initial_vector", "linear_operator", "operator_args", "num_restarts",
+                                    "krylov_dim", "pro", "pro_max_reorth", "beta_tol", "ritz_residual_tol"]
+    assert sig.parameters["num_restarts"].default == 2 and sig.parameters["krylov_dim"].default == 4
+    assert sig.parameters["beta_tol"].default == 1e-12
+    assert list(inspect.signature(qsb.ApplyMPO.forward).parameters) == ["self", "psi_flat", "L", "M1", "M2", "R", "out"]
+    assert list(inspect.signature(qsb.LeftEnvUpdate.forward).parameters) == ["self", "Lp", "M", "Ap"]
+    assert list(inspect.signature(qsb.RightEnvUpdate.forward).parameters) == ["self", "M", "Rnext", "Bp1"]
+
+
+def test_sweeps_schedule_errors():
+    with pytest.raises(ValueError):
+        qsb.Sweeps(0)
+    s = qsb.Sweeps(3)
+    assert s.maxdim == [10, 10, 10] and s.krylov_dim == [4, 4, 4] and s.cutoff == [1e-12] * 3
+    s.set_schedule(maxdim=[4, 8, 12], reortho=[False, False, True])
+    assert s.maxdim == [4, 8, 12]
+    with pytest.raises(AttributeError):
+        s.set_schedule(nope=[1, 2, 3])
+    with pytest.raises(ValueError):
+        s.set_schedule(maxdim=[1, 2])
+    assert "maxdim: [4, 8, 12]" in repr(s)
+
+
+def test_backend_names():
+    for b in ("auto", "einsum", "ncon"):
+        qsb.ApplyMPO(b)
+    with pytest.raises(ValueError):
+        qsb.ApplyMPO("cutensor")
+    with pytest.raises(ValueError):
+        qsb.set_contract_backend("nope", "cuda")
+
+
+def test_no_cpu_fallback():
+    L = torch.ones(1, 1, 1, dtype=torch.float64)
+    M = torch.ones(1, 1, 2, 2, dtype=torch.float64)
+    with pytest.raises(RuntimeError):          # NotImplementedError is a RuntimeError; never TypeError
+        qsb.ApplyMPO()(torch.ones(4, dtype=torch.float64), L, M, M, L)
+    with pytest.raises(RuntimeError):
+        qsb.lanczos_ground_state(torch.ones(4, dtype=torch.float64), lambda x, A: A @ x, (torch.eye(4, dtype=torch.float64),))
+    with pytest.raises(RuntimeError):
+        mps = qsb.MPS(4, 2, 4, "cpu", torch.float64, seed=1)
+        qsb.DMRG(mps, [M] * 4, device="cpu")
+
+
+def test_environment_manager_boundaries_and_errors():
+    mpo = [torch.zeros(1, 3, 2, 2), torch.zeros(3, 3, 2, 2), torch.zeros(3, 1, 2, 2)]
+    env = qsb.EnvironmentManager(mpo, "cpu", torch.float64)
+    assert tuple(env.get_L(0).shape) == (1, 1, 1) and tuple(env.get_R(3).shape) == (1, 1, 1)
+    with pytest.raises(RuntimeError, match=r"L\[1\] requested"):
+        env.get_L(1)
+    with pytest.raises(RuntimeError, match=r"R\[0\] requested"):
+        env.get_R(0)
+
+
+def test_mps_matches_reference_init():
+    """Our MPS built on the CPU with a seed is the reference's (golden init_abs_sums from the real MPS class)."""
+    import numpy as np
+    from conftest import load_golden
+    z = load_golden("dmrg")
+    for name in ("nb02_tfim_L6", "cal_heis_L20", "c1_xxz_L20_chi64_f64"):
+        L, d, chi0, seed, _ = (int(x) for x in z[f"{name}/cfg"])
+        dt = torch.complex128 if str(z[f"{name}/dtype"]) == "c128" else torch.float64
+        mps = qsb.MPS(L, d, chi0, "cpu", dt, seed=seed)
+        sums = np.array([t.detach().abs().sum().item() for t in mps.B])
+        assert np.allclose(sums, z[f"{name}/init_abs_sums"], rtol=1e-13, atol=0)
+        assert mps.ortho_center == 0 and len(mps.sWeight) == L + 1
