@@ -1,11 +1,417 @@
-// TMA-staged variant of the FP64 DMMA GEMM core (aligned operands).  See gemm.cu for the contract.
+// TMA-staged FP64 tensor-core (DMMA.8x8x4) GEMM -- the production path for aligned operands.
+//
+//   C[z][m][n] = sum_p sum_k opA(A[z,p][m][k]) * opB(B[z,p][k][n])          (contract: gemm.cu)
+//
+// * One cp.async.bulk.tensor (TMA) per operand per pipeline stage, issued by one elected thread, completion on
+//   an mbarrier (expect-tx); a second mbarrier per stage (one arrival per warp) hands the slot back.  The
+//   refill runs two iterations behind the consumers, so the issuing thread practically never waits.
+// * Shared-memory tiles use the hardware 128-byte swizzle.  Fragment rows/columns are assigned to lanes through
+//   small permutations (sigma / pos0 / rho below) chosen so that every LDS.64 (float64) or LDS.128 (complex128)
+//   fragment load is bank-conflict free for both operand orientations; the permutation only renames which
+//   output row/column a lane owns, which the epilogue undoes.
+// * Either dimension of A and of B may be the contiguous one:
+//     "KC"  k contiguous      : tensor map [k, r, p, z],           box [128 B of k, tile rows]
+//     "RC"  row idx contiguous: tensor map [r_lo, k, r_hi, p, z],  box [128 B of r, BK, tile rows / r_lo]
+//   complex128 is described to the TMA as float64 with a doubled innermost extent.
+// * Out-of-range k (and rows of KC operands) are zero-filled by the TMA, so ragged extents need no copies.
 #include "common.cuh"
+#include <mutex>
 
 namespace qsb {
 
+template <bool CPLX> struct TCfg;
+template <> struct TCfg<false> {
+    static constexpr int ES = 8, BM = 128, BN = 128, BK = 16;
+    static constexpr int WARPS_M = 2, WARPS_N = 4, WM = 64, WN = 32;
+    static constexpr int STAGES = 6;
+    static constexpr int RLO = 16;                  // elements per 128-byte line
+};
+template <> struct TCfg<true> {
+    static constexpr int ES = 16, BM = 128, BN = 64, BK = 8;
+    static constexpr int WARPS_M = 4, WARPS_N = 2, WM = 32, WN = 32;
+    static constexpr int STAGES = 8;
+    static constexpr int RLO = 8;
+};
+constexpr int kTmaThreads = 256;
+
+struct TArgs {
+    int M, N, K, P;
+    int tiles_m, tiles_n;
+    int a_has_p, a_has_z, b_has_p, b_has_z;     // 0 when that stride is 0 (coordinate pinned to 0)
+    char* C; long long c_ms, c_ns, c_zs;
+    double sgnA, sgnB;
+};
+
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) { }
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        :: "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+
+// lane -> fragment-row permutations (see header comment)
+__device__ __forceinline__ int perm_sigma(int g) { return 2 * (g & 3) + (g >> 2); }               // f64, KC
+__device__ __forceinline__ int perm_pos0(int g) { return (g & 1) + 8 * ((g >> 1) & 1) + 2 * (g >> 2); }  // f64, RC
+__device__ __forceinline__ int perm_rho(int g) { return (g >> 1) | ((g & 1) << 2); }               // c128
+
+// index (inside the warp tile) of fragment i, lane group g
+template <bool CPLX, bool KC>
+__device__ __forceinline__ int frag_index(int i, int g) {
+    if constexpr (CPLX) return 8 * i + perm_rho(g);
+    else if constexpr (KC) return 8 * i + perm_sigma(g);
+    else return 16 * (i >> 1) + 4 * (i & 1) + perm_pos0(g);
+}
+
+// Per-thread smem addressing of one operand: offset(i, s) = base + imm(i, s) + tab[sel(i, s)]
+template <bool CPLX, bool KC> struct FragAddr {
+    uint32_t base;
+    uint32_t tab[4];
+    __device__ __forceinline__ void init(int w0, int g, int t) {
+        if constexpr (!CPLX && KC) {
+            const int sg = perm_sigma(g);
+            base = (uint32_t)((w0 + sg) * 128 + (t & 1) * 8);
+#pragma unroll
+            for (int s = 0; s < 4; ++s) tab[s] = (uint32_t)((((2 * s) ^ (sg & 6)) | ((t >> 1) ^ (sg & 1))) << 4);
+        } else if constexpr (!CPLX && !KC) {
+            const int ph = 4 * ((g >> 1) & 1) + (g >> 2);
+            base = (uint32_t)((w0 / 16) * 2048 + t * 128 + (g & 1) * 8);
+#pragma unroll
+            for (int ih = 0; ih < 2; ++ih)
+#pragma unroll
+                for (int sl = 0; sl < 2; ++sl) tab[ih * 2 + sl] = (uint32_t)(((ph | (2 * ih)) ^ (4 * sl + t)) << 4);
+        } else if constexpr (CPLX && KC) {
+            const int rg = perm_rho(g);
+            base = (uint32_t)((w0 + rg) * 128);
+            tab[0] = (uint32_t)((t ^ rg) << 4);
+            tab[1] = (uint32_t)(((4 + t) ^ rg) << 4);
+            tab[2] = tab[3] = 0;
+        } else {
+            const int rg = perm_rho(g);
+            base = (uint32_t)((w0 / 8) * 1024 + t * 128);
+            tab[0] = (uint32_t)((t ^ rg) << 4);
+            tab[1] = (uint32_t)(((4 + t) ^ rg) << 4);
+            tab[2] = tab[3] = 0;
+        }
+    }
+    // byte offset of fragment i at k4-step s inside the operand tile
+    __device__ __forceinline__ uint32_t at(int i, int s) const {
+        if constexpr (!CPLX && KC) return base + (uint32_t)(i * 1024) + tab[s];
+        else if constexpr (!CPLX && !KC) return base + (uint32_t)((i >> 1) * 2048 + s * 512) + tab[(i & 1) * 2 + (s & 1)];
+        else if constexpr (CPLX && KC) return base + (uint32_t)(i * 1024) + tab[s];
+        else return base + (uint32_t)(i * 1024 + s * 512) + tab[s];
+    }
+};
+
+template <bool CPLX, bool A_KC, bool B_KC>
+__global__ void __launch_bounds__(kTmaThreads, 1)
+gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TArgs g) {
+    using C = TCfg<CPLX>;
+    constexpr int A_BYTES = C::BM * C::BK * C::ES;
+    constexpr int B_BYTES = C::BN * C::BK * C::ES;
+    constexpr int STAGE = A_BYTES + B_BYTES;
+    constexpr int S = C::STAGES;
+    constexpr int MI = C::WM / 8, NJ = C::WN / 8, KS = C::BK / 4;
+    constexpr int ACC = CPLX ? 4 : 2;
+
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t bar_full = sbase + S * STAGE;            // S barriers, then S "empty" barriers
+    const uint32_t bar_empty = bar_full + S * 8;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g8 = lane >> 2, t4 = lane & 3;
+    const int wm0 = (warp / C::WARPS_N) * C::WM;
+    const int wn0 = (warp % C::WARPS_N) * C::WN;
+
+    int bid = blockIdx.x;
+    const int tm = bid % g.tiles_m; bid /= g.tiles_m;
+    const int tn = bid % g.tiles_n;
+    const int z = bid / g.tiles_n;
+    const int m0 = tm * C::BM, n0 = tn * C::BN;
+
+    const int ktiles = (g.K + C::BK - 1) / C::BK;
+    const int iters = ktiles * g.P;
+
+    if (tid == 0) {
+        tma_prefetch_desc(&mapA);
+        tma_prefetch_desc(&mapB);
+#pragma unroll
+        for (int s = 0; s < S; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, kTmaThreads / 32); }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    constexpr int KMUL = CPLX ? 2 : 1;       // innermost TMA coordinate is in float64 units
+    auto issue = [&](int j) {                // one thread: fill slot j % S with k-tile j
+        const int p = j / ktiles, k0 = (j - p * ktiles) * C::BK;
+        const int slot = j % S;
+        const uint32_t sa = sbase + slot * STAGE, sb = sa + A_BYTES, bar = bar_full + 8 * slot;
+        mbar_expect_tx(bar, STAGE);
+        if constexpr (A_KC) tma_load_4d(sa, &mapA, bar, k0 * KMUL, m0, g.a_has_p ? p : 0, g.a_has_z ? z : 0);
+        else tma_load_5d(sa, &mapA, bar, 0, k0, m0 / C::RLO, g.a_has_p ? p : 0, g.a_has_z ? z : 0);
+        if constexpr (B_KC) tma_load_4d(sb, &mapB, bar, k0 * KMUL, n0, g.b_has_p ? p : 0, g.b_has_z ? z : 0);
+        else tma_load_5d(sb, &mapB, bar, 0, k0, n0 / C::RLO, g.b_has_p ? p : 0, g.b_has_z ? z : 0);
+    };
+
+    if (tid == 0) {
+        for (int j = 0; j < S - 2 && j < iters; ++j) issue(j);
+    }
+
+    double acc[MI][NJ][ACC];
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+#pragma unroll
+            for (int q = 0; q < ACC; ++q) acc[i][j][q] = 0.0;
+
+    FragAddr<CPLX, A_KC> fa; fa.init(wm0, g8, t4);
+    FragAddr<CPLX, B_KC> fb; fb.init(wn0, g8, t4);
+
+    for (int it = 0; it < iters; ++it) {
+        if (tid == 0) {
+            const int j = it + S - 2;
+            if (j < iters) {
+                if (j >= S) mbar_wait_spin(bar_empty + 8 * (j % S), ((j / S) + 1) & 1);
+                issue(j);
+            }
+        }
+        const int slot = it % S;
+        mbar_wait_spin(bar_full + 8 * slot, (it / S) & 1);
+        const unsigned char* sa = smem + slot * STAGE;
+        const unsigned char* sb = sa + A_BYTES;
+        if constexpr (!CPLX) {
+            double a[2][MI], b[2][NJ];
+#pragma unroll
+            for (int i = 0; i < MI; ++i) a[0][i] = *reinterpret_cast<const double*>(sa + fa.at(i, 0));
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) b[0][j] = *reinterpret_cast<const double*>(sb + fb.at(j, 0));
+#pragma unroll
+            for (int kk = 0; kk < KS; ++kk) {
+                const int cur = kk & 1, nxt = cur ^ 1;
+                if (kk + 1 < KS) {
+#pragma unroll
+                    for (int i = 0; i < MI; ++i) a[nxt][i] = *reinterpret_cast<const double*>(sa + fa.at(i, kk + 1));
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) b[nxt][j] = *reinterpret_cast<const double*>(sb + fb.at(j, kk + 1));
+                }
+#pragma unroll
+                for (int i = 0; i < MI; ++i)
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[cur][i], b[cur][j]);
+            }
+        } else {
+            double2 a[2][MI], b[2][NJ];
+#pragma unroll
+            for (int i = 0; i < MI; ++i) a[0][i] = *reinterpret_cast<const double2*>(sa + fa.at(i, 0));
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) b[0][j] = *reinterpret_cast<const double2*>(sb + fb.at(j, 0));
+#pragma unroll
+            for (int kk = 0; kk < KS; ++kk) {
+                const int cur = kk & 1, nxt = cur ^ 1;
+                if (kk + 1 < KS) {
+#pragma unroll
+                    for (int i = 0; i < MI; ++i) a[nxt][i] = *reinterpret_cast<const double2*>(sa + fa.at(i, kk + 1));
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) b[nxt][j] = *reinterpret_cast<const double2*>(sb + fb.at(j, kk + 1));
+                }
+                double ai[MI], nai[MI], bi[NJ];
+#pragma unroll
+                for (int i = 0; i < MI; ++i) { ai[i] = a[cur][i].y * g.sgnA; nai[i] = -ai[i]; }
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) bi[j] = b[cur][j].y * g.sgnB;
+#pragma unroll
+                for (int i = 0; i < MI; ++i)
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) {
+                        dmma884(acc[i][j][0], acc[i][j][1], a[cur][i].x, b[cur][j].x);
+                        dmma884(acc[i][j][2], acc[i][j][3], a[cur][i].x, bi[j]);
+                    }
+#pragma unroll
+                for (int i = 0; i < MI; ++i)
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) {
+                        dmma884(acc[i][j][0], acc[i][j][1], nai[i], bi[j]);
+                        dmma884(acc[i][j][2], acc[i][j][3], ai[i], b[cur][j].x);
+                    }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty + 8 * slot);
+    }
+
+    // epilogue: lane owns rows frag_index<A>(i, g8) and columns frag_index<B>(j, 2*t4), frag_index<B>(j, 2*t4+1)
+    char* Cz = g.C + g.c_zs * z * C::ES;
+    bool vec_ok = false;
+    if constexpr (!CPLX && !B_KC)        // RC columns come in adjacent pairs -> 16-byte stores
+        vec_ok = (g.c_ns == 1) && ((g.c_ms & 1) == 0) && ((g.c_zs & 1) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15u) == 0);
+#pragma unroll
+    for (int i = 0; i < MI; ++i) {
+        const int m = m0 + wm0 + frag_index<CPLX, A_KC>(i, g8);
+        if (m >= g.M) continue;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const int c0 = n0 + wn0 + frag_index<CPLX, B_KC>(j, 2 * t4);
+            const int c1 = n0 + wn0 + frag_index<CPLX, B_KC>(j, 2 * t4 + 1);
+            char* row = Cz + g.c_ms * m * C::ES;
+            if constexpr (!CPLX) {
+                if (vec_ok && c1 < g.N) {        // c1 == c0 + 1 for the RC permutation
+                    *reinterpret_cast<double2*>(row + (long long)c0 * C::ES) = make_double2(acc[i][j][0], acc[i][j][1]);
+                } else {
+                    if (c0 < g.N) *reinterpret_cast<double*>(row + g.c_ns * c0 * C::ES) = acc[i][j][0];
+                    if (c1 < g.N) *reinterpret_cast<double*>(row + g.c_ns * c1 * C::ES) = acc[i][j][1];
+                }
+            } else {
+                if (c0 < g.N) *reinterpret_cast<double2*>(row + g.c_ns * c0 * C::ES) = make_double2(acc[i][j][0], acc[i][j][2]);
+                if (c1 < g.N) *reinterpret_cast<double2*>(row + g.c_ns * c1 * C::ES) = make_double2(acc[i][j][1], acc[i][j][3]);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host: tensor-map construction and dispatch
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+        (void)cudaGetLastError();
+    });
+    return fn;
+}
+
+struct Operand {
+    const void* ptr; long long rs, ks, ps, zs;   // element strides (rs: row index m or n)
+    int rows, has_p, has_z;
+};
+
+// Can this operand be described to the TMA?  (16-byte aligned base and strides; RC rows a multiple of a line)
+static bool tma_eligible(const Operand& o, bool cplx, bool kc, int K, int P, int Z) {
+    const long long es = cplx ? 16 : 8;
+    if (!aligned16(o.ptr)) return false;
+    auto ok = [&](long long st) { return st > 0 && (st * es) % 16 == 0 && st * es < (1LL << 40); };
+    if (kc) { if (o.rows > 1 && !ok(o.rs)) return false; }
+    else {
+        const int rlo = cplx ? 8 : 16;
+        if (o.rows % rlo != 0) return false;
+        if (K > 1 && !ok(o.ks)) return false;
+    }
+    if (o.has_p && P > 1 && !ok(o.ps)) return false;
+    if (o.has_z && Z > 1 && !ok(o.zs)) return false;
+    return true;
+}
+
+static bool make_map(CUtensorMap* map, const Operand& o, bool cplx, bool kc, int tile_rows, int BK, int K, int P,
+                     int Z) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    const long long es = cplx ? 16 : 8;
+    const int kmul = cplx ? 2 : 1;
+    const int rlo = cplx ? 8 : 16;
+    cuuint64_t dims[5]; cuuint64_t strides[4]; cuuint32_t box[5]; cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const cuuint64_t np = (o.has_p && P > 1) ? (cuuint64_t)P : 1, nz = (o.has_z && Z > 1) ? (cuuint64_t)Z : 1;
+    // strides of extent-1 dimensions are never used for addressing, but must still be valid (16-byte multiples)
+    auto st = [&](long long s, bool used) { return (cuuint64_t)((used ? s : 2) * es); };
+    int rank;
+    if (kc) {
+        rank = 4;
+        dims[0] = (cuuint64_t)K * kmul; dims[1] = (cuuint64_t)o.rows; dims[2] = np; dims[3] = nz;
+        strides[0] = st(o.rs, o.rows > 1); strides[1] = st(o.ps, np > 1); strides[2] = st(o.zs, nz > 1);
+        box[0] = (cuuint32_t)(BK * kmul); box[1] = (cuuint32_t)tile_rows; box[2] = 1; box[3] = 1;
+    } else {
+        rank = 5;
+        dims[0] = (cuuint64_t)rlo * kmul; dims[1] = (cuuint64_t)K; dims[2] = (cuuint64_t)(o.rows / rlo);
+        dims[3] = np; dims[4] = nz;
+        strides[0] = st(o.ks, K > 1); strides[1] = (cuuint64_t)(rlo * es); strides[2] = st(o.ps, np > 1);
+        strides[3] = st(o.zs, nz > 1);
+        box[0] = (cuuint32_t)(rlo * kmul); box[1] = (cuuint32_t)BK; box[2] = (cuuint32_t)(tile_rows / rlo);
+        box[3] = 1; box[4] = 1;
+    }
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)rank, const_cast<void*>(o.ptr), dims, strides,
+                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+template <bool CPLX, bool A_KC, bool B_KC>
+static int launch_tma(const CUtensorMap& ma, const CUtensorMap& mb, const TArgs& t, int Z, cudaStream_t stream) {
+    using C = TCfg<CPLX>;
+    auto kern = gemm_tma_kernel<CPLX, A_KC, B_KC>;
+    constexpr int SMEM = C::STAGES * (C::BM + C::BN) * C::BK * C::ES + 2 * C::STAGES * 8 + 1024;
+    static bool configured = false;
+    if (!configured) {
+        int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        if (rc) return rc;
+        configured = true;
+    }
+    const long long blocks = (long long)t.tiles_m * t.tiles_n * Z;
+    if (blocks > 2147483647LL) return QSB_ERR_SHAPE;
+    kern<<<(unsigned)blocks, kTmaThreads, SMEM, stream>>>(ma, mb, t);
+    ++g_count_tma;
+    return check_launch();
+}
+
 int gemm_tma_try(const GemmArgs& g, cudaStream_t stream, bool* used) {
-    (void)g; (void)stream;
     *used = false;
+    const bool cplx = g.cplx != 0;
+    if (g.K < 1 || g.P < 1) return QSB_OK;
+    Operand a{g.A, g.a_rs, g.a_ks, g.a_ps, g.a_zs, g.M, g.a_ps != 0, g.a_zs != 0};
+    Operand b{g.B, g.b_rs, g.b_ks, g.b_ps, g.b_zs, g.N, g.b_ps != 0, g.b_zs != 0};
+    // orientation: prefer k-contiguous when both strides are 1 (extent-1 dimensions)
+    const bool a_kc = (a.ks == 1 || g.K == 1), b_kc = (b.ks == 1 || g.K == 1);
+    if (!a_kc && a.rs != 1) return QSB_OK;
+    if (!b_kc && b.rs != 1) return QSB_OK;
+    if (a_kc && g.K == 1) a.ks = 1;
+    if (b_kc && g.K == 1) b.ks = 1;
+    if (!tma_eligible(a, cplx, a_kc, g.K, g.P, g.Z) || !tma_eligible(b, cplx, b_kc, g.K, g.P, g.Z)) return QSB_OK;
+    if (!aligned16(g.C)) return QSB_OK;
+    const int BM = cplx ? TCfg<true>::BM : TCfg<false>::BM, BN = cplx ? TCfg<true>::BN : TCfg<false>::BN;
+    const int BK = cplx ? TCfg<true>::BK : TCfg<false>::BK;
+    CUtensorMap ma, mb;
+    if (!make_map(&ma, a, cplx, a_kc, BM, BK, g.K, g.P, g.Z)) return QSB_OK;
+    if (!make_map(&mb, b, cplx, b_kc, BN, BK, g.K, g.P, g.Z)) return QSB_OK;
+
+    TArgs t;
+    t.M = g.M; t.N = g.N; t.K = g.K; t.P = g.P;
+    t.tiles_m = (g.M + BM - 1) / BM; t.tiles_n = (g.N + BN - 1) / BN;
+    t.a_has_p = (a.has_p && g.P > 1); t.a_has_z = (a.has_z && g.Z > 1);
+    t.b_has_p = (b.has_p && g.P > 1); t.b_has_z = (b.has_z && g.Z > 1);
+    t.C = (char*)g.C; t.c_ms = g.c_ms; t.c_ns = g.c_ns; t.c_zs = g.Z > 1 ? g.c_zs : 0;
+    t.sgnA = g.conjA ? -1.0 : 1.0; t.sgnB = g.conjB ? -1.0 : 1.0;
+    int rc;
+    if (cplx) {
+        if (a_kc) rc = b_kc ? launch_tma<true, true, true>(ma, mb, t, g.Z, stream) : launch_tma<true, true, false>(ma, mb, t, g.Z, stream);
+        else rc = b_kc ? launch_tma<true, false, true>(ma, mb, t, g.Z, stream) : launch_tma<true, false, false>(ma, mb, t, g.Z, stream);
+    } else {
+        if (a_kc) rc = b_kc ? launch_tma<false, true, true>(ma, mb, t, g.Z, stream) : launch_tma<false, true, false>(ma, mb, t, g.Z, stream);
+        else rc = b_kc ? launch_tma<false, false, true>(ma, mb, t, g.Z, stream) : launch_tma<false, false, false>(ma, mb, t, g.Z, stream);
+    }
+    if (rc) return rc;
+    *used = true;
     return QSB_OK;
 }
 

@@ -42,6 +42,42 @@ def test_gemm_core_all_layouts(dtype, shape, ta, tb):
         assert rel_err(out, torch.matmul(A.conj(), B.conj())) <= TOL
 
 
+@pytest.mark.parametrize("dtype", [torch.float64, torch.complex128])
+@pytest.mark.parametrize("shape", [(2, 256, 128, 64), (1, 144, 80, 100), (3, 128, 64, 8), (1, 16, 16, 4),
+                                   (1, 400, 272, 130), (5, 512, 1024, 512)])
+@pytest.mark.parametrize("ta,tb", [(False, False), (True, False), (False, True), (True, True)])
+def test_gemm_core_tma_path(dtype, shape, ta, tb):
+    """Aligned operands must take the TMA-staged kernel (force_path=1 errors out if they cannot) and agree
+    with the cp.async kernel (force_path=2) and with torch."""
+    Z, M, N, K = shape
+    A = randn((Z, M, K), dtype, 3)
+    B = randn((Z, K, N), dtype, 4)
+    ref = torch.matmul(A, B)
+    Ad = (A.transpose(1, 2).contiguous().transpose(1, 2) if ta else A).to(DEV)
+    Bd = (B.transpose(1, 2).contiguous().transpose(1, 2) if tb else B).to(DEV)
+    before = qsb.launch_counters()["tma_gemm"]
+    out = _lib.gemm(Ad, Bd, force_path=1)
+    assert qsb.launch_counters()["tma_gemm"] == before + 1
+    assert rel_err(out, ref) <= TOL
+    out2 = _lib.gemm(Ad, Bd, force_path=2)
+    assert rel_err(out2, ref) <= TOL
+    if dtype.is_complex:
+        out = _lib.gemm(Ad, Bd, conjA=True, conjB=False, force_path=1)
+        assert rel_err(out, torch.matmul(A.conj(), B)) <= TOL
+
+
+def test_gemm_unaligned_falls_back_to_cpasync():
+    A = randn((1, 33, 17), torch.float64, 5).to(DEV)
+    B = randn((1, 17, 9), torch.float64, 6).to(DEV)
+    before = qsb.launch_counters()
+    out = _lib.gemm(A, B)
+    after = qsb.launch_counters()
+    assert after["cpasync_gemm"] == before["cpasync_gemm"] + 1 and after["tma_gemm"] == before["tma_gemm"]
+    assert rel_err(out, torch.matmul(A, B)) <= TOL
+    with pytest.raises(ValueError):
+        _lib.gemm(A, B, force_path=1)
+
+
 # ----------------------------------------------------------------------------- H_eff matvec
 @pytest.mark.parametrize("name", _names(load_golden("matvec")))
 def test_matvec_golden(name):
