@@ -52,7 +52,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) { }
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();     // ~2 s: a lost TMA completion must fail loudly, not hang
+    }
 }
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
                                             int c0, int c1, int c2, int c3, int c4) {
