@@ -112,6 +112,24 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" :: "l"(map) : "memory");
 }
 
+// ---- tile rasterisation -------------------------------------------------------
+// Linear CTA index -> (tile_m, tile_n, batch z).  Tiles are walked in groups of kRasterGroup rows of tiles, n
+// fastest inside a group, so that one wave of 148 CTAs covers a ~12 x 12 patch: the A and B panels a wave streams
+// from HBM are ~2 * sqrt(148) instead of tiles_m + 148 / tiles_m (L2-friendly rasterisation).
+constexpr int kRasterGroup = 12;
+__device__ __forceinline__ void tile_coords(int bid, int tiles_m, int tiles_n, int& tm, int& tn, int& z) {
+    const int per_z = tiles_m * tiles_n;
+    z = bid / per_z;
+    const int r = bid - z * per_z;
+    const int per_group = kRasterGroup * tiles_n;
+    const int grp = r / per_group;
+    const int first = grp * kRasterGroup;
+    const int gsz = min(kRasterGroup, tiles_m - first);
+    const int rr = r - grp * per_group;
+    tn = rr / gsz;
+    tm = first + (rr - tn * gsz);
+}
+
 // ---- reductions -------------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

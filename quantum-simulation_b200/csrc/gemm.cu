@@ -116,11 +116,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_cpasync(const KArgs g) {
     const int wm0 = (warp / C::WARPS_N) * C::WM;
     const int wn0 = (warp % C::WARPS_N) * C::WN;
 
-    // tile coordinates: m fastest, then n, then batch z
-    int bid = blockIdx.x;
-    const int tm = bid % g.tiles_m; bid /= g.tiles_m;
-    const int tn = bid % g.tiles_n;
-    const int z = bid / g.tiles_n;
+    int tm, tn, z;
+    tile_coords(blockIdx.x, g.tiles_m, g.tiles_n, tm, tn, z);
     const int m0 = tm * C::BM, n0 = tn * C::BN;
 
     const char* Az = g.A + (g.a_zs * z + g.a_rs * m0) * C::ES;

@@ -141,10 +141,8 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     const int wm0 = (warp / C::WARPS_N) * C::WM;
     const int wn0 = (warp % C::WARPS_N) * C::WN;
 
-    int bid = blockIdx.x;
-    const int tm = bid % g.tiles_m; bid /= g.tiles_m;
-    const int tn = bid % g.tiles_n;
-    const int z = bid / g.tiles_n;
+    int tm, tn, z;
+    tile_coords(blockIdx.x, g.tiles_m, g.tiles_n, tm, tn, z);
     const int m0 = tm * C::BM, n0 = tn * C::BN;
 
     const int ktiles = (g.K + C::BK - 1) / C::BK;

@@ -1,0 +1,139 @@
+#!/usr/bin/env python3
+"""Sweep-level measurements (BASELINE.json: "DMRG sweep time"): full DMRG runs through the drop-in DMRG class on
+the GPU, energy parity against the CPU oracle where it finishes in seconds, and a per-bond-step breakdown at
+chi = 2048.  Prints one JSON object per case.  Usage: python tools/sweep_bench.py [c1] [c2] [c3] [svd]"""
+import contextlib
+import io
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import quantum_simulation_b200 as qsb          # noqa: E402
+from oracle import dmrg_oracle as orc          # noqa: E402
+
+DEV = "cuda"
+
+
+def mpo(key, dtype):
+    z = np.load(os.path.join(ROOT, "tests", "golden", "mpo.npz"))
+    return [torch.from_numpy(z[f"{key}/t{int(u)}"]).to(dtype).contiguous() for u in z[f"{key}/index"]]
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def run_gpu(key, L, chi, dtype, nsweeps, seed=1, krylov=4, maxit=2):
+    mps = quiet(qsb.MPS, L, 2, chi, "cpu", dtype, seed).to(DEV)
+    sw = qsb.Sweeps(nsweeps)
+    sw.set_schedule(maxdim=[chi] * nsweeps, cutoff=[0.0] * nsweeps, krylov_dim=[krylov] * nsweeps,
+                    noise=[0.0] * nsweeps)
+    dm = quiet(qsb.DMRG, mps, [m.to(DEV) for m in mpo(key, dtype)], device=DEV, dtype=dtype)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    E, _ = quiet(dm, sw, dispon=0, maxit=maxit)
+    torch.cuda.synchronize()
+    return np.array(E), time.perf_counter() - t0, dm
+
+
+def run_cpu(key, L, chi, dtype, nsweeps, seed=1, krylov=4, maxit=2):
+    torch.set_num_threads(os.cpu_count() or 1)
+    mps = orc.OracleMPS(L, 2, chi, dtype, seed)
+    t0 = time.perf_counter()
+    E, h = orc.dmrg_run(mps, mpo(key, dtype), numsweeps=nsweeps, maxdim=[chi] * nsweeps, krylov_dim=[krylov] * nsweeps,
+                        cutoff=[0.0] * nsweeps, reortho=[False] * nsweeps, maxreortho=[1] * nsweeps, maxit=maxit)
+    return np.array(E), time.perf_counter() - t0
+
+
+def case_c1():
+    """BASELINE config 1: XXZ chain L=20, chi=64, full run on both sides."""
+    out = []
+    for key, dt in (("xxz_c128_L20", torch.complex128), ("xxz_f64_L20", torch.float64)):
+        run_gpu(key, 20, 64, dt, 1)                       # warm-up (workspaces, cuSOLVER handles)
+        Eg, tg, dm = run_gpu(key, 20, 64, dt, 3)
+        Ec, tc = run_cpu(key, 20, 64, dt, 3)
+        nb = len(Eg) // 3
+        rel = np.abs(Eg - Ec) / np.abs(Ec)
+        out.append({"case": "C1 XXZ L=20 chi=64, 3 sweeps", "mpo": key, "gpu_s": tg, "cpu_oracle_s": tc,
+                    "cpu_cores": os.cpu_count(), "gpu_s_per_sweep": tg / 3, "cpu_s_per_sweep": tc / 3,
+                    "E_final_gpu": float(Eg[-1]), "E_final_cpu": float(Ec[-1]),
+                    "max_rel_dev_all_updates": float(rel.max()),
+                    "rel_dev_end_of_sweep": [float(rel[(k + 1) * nb - 1]) for k in range(3)]})
+    return out
+
+
+def case_c2():
+    """BASELINE config 2: TFIM L=100, chi=512, 10 sweeps on the GPU; 1 oracle sweep on the CPU for the ratio."""
+    key, dt = "tfim_c128_L100_g0.5", torch.complex128
+    Eg, tg, dm = run_gpu(key, 100, 512, dt, 10)
+    res = {"case": "C2 TFIM L=100 g=0.5 chi=512, 10 sweeps", "mpo": key, "gpu_s": tg, "gpu_s_per_sweep": tg / 10,
+           "E_final_gpu": float(Eg[-1]), "bond_dim_mid": dm.history["bond_dims"][-50],
+           "E_end_of_sweep": [float(Eg[(k + 1) * 198 - 1]) for k in range(10)]}
+    if "--cpu" in sys.argv:
+        Ec, tc = run_cpu(key, 100, 512, dt, 1)
+        res.update({"cpu_oracle_s_first_sweep": tc, "cpu_cores": os.cpu_count(),
+                    "max_rel_dev_first_sweep": float((np.abs(Eg[:198] - Ec) / np.abs(Ec)).max())})
+    return [res]
+
+
+def time_it(fn, reps=3):
+    fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        fn()
+        torch.cuda.synchronize()
+        ts.append(time.perf_counter() - t0)
+    return min(ts)
+
+
+def case_svd():
+    """The non-hot-path cost that dominates a chi=2048 sweep: SVD of theta (chi*d x d*chi)."""
+    out = []
+    for n in (1024, 2048, 4096):
+        a = torch.randn(n, n, dtype=torch.float64, device=DEV)
+        row = {"case": f"svd {n}x{n} f64"}
+        for drv in (None, "gesvdj", "gesvda"):
+            try:
+                row[str(drv)] = time_it(lambda: torch.linalg.svd(a, full_matrices=False, driver=drv), 1)
+            except Exception as ex:
+                row[str(drv)] = repr(ex)[:80]
+        row["eigh_gram"] = time_it(lambda: torch.linalg.eigh(a @ a.T), 1)
+        row["qr"] = time_it(lambda: torch.linalg.qr(a), 1)
+        out.append(row)
+    return out
+
+
+def case_c3():
+    """Per-bond-step breakdown at BASELINE config 3 (Heisenberg L=100, chi=2048, f64): one bulk bond step."""
+    import bench
+    chi, dt = 2048, torch.float64
+    L, M1, M2, R, theta = bench.make_inputs(chi, dt, torch.device(DEV))
+    L = L + L.transpose(1, 2)
+    R = R + R.transpose(1, 2)
+    op = qsb.ApplyMPO()
+    t_l = time_it(lambda: qsb.lanczos_ground_state(theta, op, (L, M1, M2, R), num_restarts=2, krylov_dim=4), 2)
+    A = torch.randn(chi, 2, chi, dtype=dt, device=DEV)
+    t_e = time_it(lambda: qsb.LeftEnvUpdate()(L, M1, A), 2)
+    t_th = time_it(lambda: torch.matmul(A.reshape(chi * 2, chi), A.reshape(chi, 2 * chi)), 2)
+    th = theta.view(chi * 2, 2 * chi)
+    t_svd = time_it(lambda: torch.linalg.svd(th, full_matrices=False), 1)
+    step = t_l + t_e + t_th + t_svd
+    return [{"case": "C3 Heisenberg L=100 chi=2048 f64: one bulk bond step", "lanczos_8_matvecs_s": t_l,
+             "env_update_s": t_e, "theta_build_s": t_th, "svd_torch_default_s": t_svd, "bond_step_s": step,
+             "sweep_198_steps_estimate_s": 198 * step, "hot_path_share": (t_l + t_e) / step}]
+
+
+if __name__ == "__main__":
+    which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["c1"]
+    for w in which:
+        for row in {"c1": case_c1, "c2": case_c2, "c3": case_c3, "svd": case_svd}[w]():
+            print(json.dumps(row), flush=True)
