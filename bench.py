@@ -375,7 +375,7 @@ def extras(args, qsb, _lib, dev, dtype, L, M1, M2, R, theta, peak_tf):
 
     def vec_iter():        # the vector ops of one Krylov iteration: dot, axpy2+norm, scale  (8 n-element passes)
         ops.lz_dot(K2[1], 1, 0, ws, n, scal, 3, 1, scratch)
-        ops.lz_axpy_norm(K2, 2, n, ws, n, scal, 2, 4, scratch)
+        ops.lz_axpy_norm(K2, 2, n, ws, n, scal, 2, 4, 0, scratch)
         ops.lz_scale(ws, K2[0], n, scal, 5)
     ws.copy_(theta)
     scal[5, 0] = 1.0

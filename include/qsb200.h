@@ -116,16 +116,20 @@ double qsb_env_flops(const qsb_env_desc* d);
  */
 size_t qsb_lz_scratch_bytes(int max_vectors);
 
-/* scal[out_idx + i] = <X_i, w>  (conjugate-linear in X), i < m; X_i = X + i*ldx.
-   flags bit0: keep only the real part (alpha, lanczos_solver.py:241);
-   flags bit1: store sqrt(re) (norm, :259, with X == w, m == 1). */
+/* flag bits shared by the reductions below */
+#define QSB_LZ_REAL   1   /* keep only the real part (alpha, lanczos_solver.py:241) */
+#define QSB_LZ_SQRT   2   /* qsb_lz_dot: store sqrt(re) (norm, :259, with X == w, m == 1) */
+#define QSB_LZ_NOSQRT 4   /* axpy_norm / combine: store the SUM OF SQUARES instead of the norm -- the partial
+                             result of one row shard, to be all-reduced across GPUs before the square root */
+
+/* scal[out_idx + i] = <X_i, w>  (conjugate-linear in X), i < m; X_i = X + i*ldx. */
 int qsb_lz_dot(int dtype, int64_t n, int m, const void* X, int64_t ldx, const void* w,
                double* scal, int out_idx, int flags, void* scratch, void* stream);
 
 /* w <- w - sum_{i<m} scal[coef_idx + i] * X_i ;  scal[norm_idx] = ||w||  (if norm_idx >= 0)
    (three-term recurrence :245-247 with m <= 2, PRO projection :255-256 with m = j) */
 int qsb_lz_axpy_norm(int dtype, int64_t n, int m, const void* X, int64_t ldx, void* w,
-                     double* scal, int coef_idx, int norm_idx, void* scratch, void* stream);
+                     double* scal, int coef_idx, int norm_idx, int flags, void* scratch, void* stream);
 
 /* dst <- src / Re(scal[idx])   (v_{j+1} = w / beta :268-270, _normalize_to :154) */
 int qsb_lz_scale(int dtype, int64_t n, const void* src, void* dst, const double* scal, int idx,
@@ -133,7 +137,7 @@ int qsb_lz_scale(int dtype, int64_t n, const void* src, void* dst, const double*
 
 /* dst <- sum_{i<m} y_host[i] * X_i ; scal[norm_idx] = ||dst||   (Ritz vector :293-294) */
 int qsb_lz_combine(int dtype, int64_t n, int m, const void* X, int64_t ldx, const double* y_host,
-                   void* dst, double* scal, int norm_idx, void* scratch, void* stream);
+                   void* dst, double* scal, int norm_idx, int flags, void* scratch, void* stream);
 
 /* ---- utilities ---------------------------------------------------------- */
 /* dst (contiguous, shape dims[0..2]) <- src with element strides; optional conj */

@@ -108,9 +108,9 @@ def load() -> C.CDLL:
     lib.qsb_lz_scratch_bytes.argtypes = [i32]
     lib.qsb_lz_scratch_bytes.restype = C.c_size_t
     lib.qsb_lz_dot.argtypes = [i32, i64, i32, vp, i64, vp, vp, i32, i32, vp, vp]
-    lib.qsb_lz_axpy_norm.argtypes = [i32, i64, i32, vp, i64, vp, vp, i32, i32, vp, vp]
+    lib.qsb_lz_axpy_norm.argtypes = [i32, i64, i32, vp, i64, vp, vp, i32, i32, i32, vp, vp]
     lib.qsb_lz_scale.argtypes = [i32, i64, vp, vp, vp, i32, vp]
-    lib.qsb_lz_combine.argtypes = [i32, i64, i32, vp, i64, C.POINTER(C.c_double), vp, vp, i32, vp, vp]
+    lib.qsb_lz_combine.argtypes = [i32, i64, i32, vp, i64, C.POINTER(C.c_double), vp, vp, i32, i32, vp, vp]
     lib.qsb_strided_copy3.argtypes = [i32, C.POINTER(i64), vp, C.POINTER(i64), vp, i32, vp]
     lib.qsb_gemm.argtypes = [C.POINTER(GemmDesc), vp]
     lib.qsb_probe_dmma.argtypes = [i32, C.POINTER(C.c_double), vp, vp]
@@ -301,11 +301,12 @@ def _impl_lz_dot(X, m: int, ldx: int, w, n: int, scal, out_idx: int, flags: int,
                                 out_idx, flags, scratch.data_ptr(), _stream()), "lanczos.dot")
 
 
-def _impl_lz_axpy_norm(X, m: int, ldx: int, w, n: int, scal, coef_idx: int, norm_idx: int, scratch) -> None:
+def _impl_lz_axpy_norm(X, m: int, ldx: int, w, n: int, scal, coef_idx: int, norm_idx: int, flags: int,
+                       scratch) -> None:
     dev = _require_cuda(X, w, scal, scratch)
     with torch.cuda.device(dev):
         check(load().qsb_lz_axpy_norm(dtype_code(w.dtype), n, m, X.data_ptr(), ldx, w.data_ptr(),
-                                      scal.data_ptr(), coef_idx, norm_idx, scratch.data_ptr(), _stream()),
+                                      scal.data_ptr(), coef_idx, norm_idx, flags, scratch.data_ptr(), _stream()),
               "lanczos.axpy_norm")
 
 
@@ -316,12 +317,13 @@ def _impl_lz_scale(src, dst, n: int, scal, idx: int) -> None:
                                   _stream()), "lanczos.scale")
 
 
-def _impl_lz_combine(X, m: int, ldx: int, y: Sequence[float], dst, n: int, scal, norm_idx: int, scratch) -> None:
+def _impl_lz_combine(X, m: int, ldx: int, y: Sequence[float], dst, n: int, scal, norm_idx: int, flags: int,
+                     scratch) -> None:
     dev = _require_cuda(X, dst, scal, scratch)
     yy = (C.c_double * len(y))(*[float(v) for v in y])
     with torch.cuda.device(dev):
         check(load().qsb_lz_combine(dtype_code(dst.dtype), n, m, X.data_ptr(), ldx, yy, dst.data_ptr(),
-                                    scal.data_ptr(), norm_idx, scratch.data_ptr(), _stream()), "lanczos.combine")
+                                    scal.data_ptr(), norm_idx, flags, scratch.data_ptr(), _stream()), "lanczos.combine")
 
 
 def set_stage_events(events: Optional[Sequence[torch.cuda.Event]]) -> None:
@@ -401,10 +403,10 @@ def register_ops() -> None:
     tl.define("lz_dot(Tensor X, int m, int ldx, Tensor w, int n, Tensor(a!) scal, int out_idx, int flags, "
               "Tensor(b!) scratch) -> ()")
     tl.define("lz_axpy_norm(Tensor X, int m, int ldx, Tensor(a!) w, int n, Tensor(b!) scal, int coef_idx, "
-              "int norm_idx, Tensor(c!) scratch) -> ()")
+              "int norm_idx, int flags, Tensor(c!) scratch) -> ()")
     tl.define("lz_scale(Tensor src, Tensor(a!) dst, int n, Tensor scal, int idx) -> ()")
     tl.define("lz_combine(Tensor X, int m, int ldx, float[] y, Tensor(a!) dst, int n, Tensor(b!) scal, "
-              "int norm_idx, Tensor(c!) scratch) -> ()")
+              "int norm_idx, int flags, Tensor(c!) scratch) -> ()")
     tl.impl("heff_apply", _impl_heff_apply, "CUDA")
     tl.impl("env_left", _impl_env_left, "CUDA")
     tl.impl("env_right", _impl_env_right, "CUDA")

@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(kLzThreads) lz_dot_kernel(const T* X, long lon
 template <typename T, int MODE, int MV>
 __global__ void __launch_bounds__(kLzThreads) lz_axpy_norm_kernel(const T* X, long long ldx_units, T* w,
                                                                   long long nunits, double* scal, int coef_idx,
-                                                                  int norm_idx, Scratch* sc) {
+                                                                  int norm_idx, int flags, Scratch* sc) {
     __shared__ double sm[(kLzThreads / 32)];
     double cr[MV], ci[MV];
 #pragma unroll
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(kLzThreads) lz_axpy_norm_kernel(const T* X, lo
     block_sum<1>(v, sm);
     __syncthreads();
     grid_finish<1>(v, sc, sm, [&](double (&acc)[1]) {
-        scal[2 * norm_idx] = sqrt(acc[0]);
+        scal[2 * norm_idx] = (flags & QSB_LZ_NOSQRT) ? acc[0] : sqrt(acc[0]);
         scal[2 * norm_idx + 1] = 0.0;
     });
 }
@@ -184,7 +184,7 @@ struct CombineCoef { double y[kLzMaxCombine]; };
 template <typename T, int MODE>
 __global__ void __launch_bounds__(kLzThreads) lz_combine_kernel(const T* X, long long ldx_units, int m,
                                                                 const CombineCoef cf, T* dst, long long nunits,
-                                                                double* scal, int norm_idx, Scratch* sc) {
+                                                                double* scal, int norm_idx, int flags, Scratch* sc) {
     __shared__ double sm[(kLzThreads / 32)];
     double v[1] = {0.0};
     const long long stride = (long long)gridDim.x * kLzThreads;
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(kLzThreads) lz_combine_kernel(const T* X, long
     block_sum<1>(v, sm);
     __syncthreads();
     grid_finish<1>(v, sc, sm, [&](double (&acc)[1]) {
-        scal[2 * norm_idx] = sqrt(acc[0]);
+        scal[2 * norm_idx] = (flags & QSB_LZ_NOSQRT) ? acc[0] : sqrt(acc[0]);
         scal[2 * norm_idx + 1] = 0.0;
     });
 }
@@ -304,7 +304,7 @@ extern "C" int qsb_lz_dot(int dtype, int64_t n, int m, const void* X, int64_t ld
 }
 
 extern "C" int qsb_lz_axpy_norm(int dtype, int64_t n, int m, const void* X, int64_t ldx, void* w, double* scal,
-                                int coef_idx, int norm_idx, void* scratch, void* stream_) {
+                                int coef_idx, int norm_idx, int flags, void* scratch, void* stream_) {
     if (!lz_dtype_ok(dtype)) return QSB_ERR_DTYPE;
     if (n < 0 || m < 1 || coef_idx < 0) return QSB_ERR_ARG;
     if (!X || !w || !scal || !scratch) return QSB_ERR_ARG;
@@ -323,9 +323,9 @@ extern "C" int qsb_lz_axpy_norm(int dtype, int64_t n, int m, const void* X, int6
         const int nidx = (i0 + mv >= m) ? norm_idx : -1;    // the norm belongs to the last pass
         const char* Xi = (const char*)X + (size_t)i0 * ldx * es;
         QSB_LZ_DISPATCH(v, {
-            if (mv == 4) lz_axpy_norm_kernel<T, MODE, 4><<<grid, kLzThreads, 0, stream>>>((const T*)Xi, ldu, (T*)w, v.nunits, scal, coef_idx + i0, nidx, sc);
-            else if (mv == 2) lz_axpy_norm_kernel<T, MODE, 2><<<grid, kLzThreads, 0, stream>>>((const T*)Xi, ldu, (T*)w, v.nunits, scal, coef_idx + i0, nidx, sc);
-            else lz_axpy_norm_kernel<T, MODE, 1><<<grid, kLzThreads, 0, stream>>>((const T*)Xi, ldu, (T*)w, v.nunits, scal, coef_idx + i0, nidx, sc);
+            if (mv == 4) lz_axpy_norm_kernel<T, MODE, 4><<<grid, kLzThreads, 0, stream>>>((const T*)Xi, ldu, (T*)w, v.nunits, scal, coef_idx + i0, nidx, flags, sc);
+            else if (mv == 2) lz_axpy_norm_kernel<T, MODE, 2><<<grid, kLzThreads, 0, stream>>>((const T*)Xi, ldu, (T*)w, v.nunits, scal, coef_idx + i0, nidx, flags, sc);
+            else lz_axpy_norm_kernel<T, MODE, 1><<<grid, kLzThreads, 0, stream>>>((const T*)Xi, ldu, (T*)w, v.nunits, scal, coef_idx + i0, nidx, flags, sc);
         });
         ++g_count_other;
         int rc = check_launch();
@@ -354,7 +354,7 @@ extern "C" int qsb_lz_scale(int dtype, int64_t n, const void* src, void* dst, co
 }
 
 extern "C" int qsb_lz_combine(int dtype, int64_t n, int m, const void* X, int64_t ldx, const double* y_host,
-                              void* dst, double* scal, int norm_idx, void* scratch, void* stream_) {
+                              void* dst, double* scal, int norm_idx, int flags, void* scratch, void* stream_) {
     if (!lz_dtype_ok(dtype)) return QSB_ERR_DTYPE;
     if (n < 0 || m < 1 || m > kLzMaxCombine) return QSB_ERR_ARG;
     if (!X || !y_host || !dst || !scal || !scratch) return QSB_ERR_ARG;
@@ -368,7 +368,7 @@ extern "C" int qsb_lz_combine(int dtype, int64_t n, int m, const void* X, int64_
     for (int i = 0; i < kLzMaxCombine; ++i) cf.y[i] = i < m ? y_host[i] : 0.0;
     Scratch* sc = (Scratch*)scratch;
     QSB_LZ_DISPATCH(v, {
-        lz_combine_kernel<T, MODE><<<grid, kLzThreads, 0, stream>>>((const T*)X, ldu, m, cf, (T*)dst, v.nunits, scal, norm_idx, sc);
+        lz_combine_kernel<T, MODE><<<grid, kLzThreads, 0, stream>>>((const T*)X, ldu, m, cf, (T*)dst, v.nunits, scal, norm_idx, flags, sc);
     });
     ++g_count_other;
     return check_launch();

@@ -1,0 +1,122 @@
+"""World-size-2 gloo tests (CPU) of the multi-GPU HOST logic: the row partition, the
+all-gather exchange step of the sharded matvec and the scalar all-reduces of the sharded Lanczos.  The numerical
+engine on each rank is the oracle (matvec) / a torch vector backend, injected through the same hooks the CUDA
+path uses; the product defaults stay CUDA-only."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _problem(dtype, chi_l, chi_r, hermitian):
+    from conftest import golden_mpo
+    mpo = golden_mpo("heis_c128_L20" if dtype.is_complex else "heis_f64_L20", dtype)
+    M1, M2 = mpo[9], mpo[10]
+    g = torch.Generator().manual_seed(7)
+    L = torch.randn(5, chi_l, chi_l, dtype=dtype, generator=g)
+    R = torch.randn(5, chi_r, chi_r, dtype=dtype, generator=g)
+    if hermitian:        # physical environments are Hermitian per MPO channel pair; make H_eff Hermitian
+        L = L + L.conj().transpose(1, 2)
+        R = R + R.conj().transpose(1, 2)
+    psi = torch.randn(chi_l * 4 * chi_r, dtype=dtype, generator=g)
+    return L, M1, M2, R, psi
+
+
+def _worker(rank, world, port, chi_l, chi_r, dtype_name, result_q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.set_num_threads(2)
+        import quantum_simulation_b200 as qsb
+        from quantum_simulation_b200 import parallel
+        from oracle import dmrg_oracle as orc
+        from vecops_torch import TorchVectorOps
+        dtype = getattr(torch, dtype_name)
+        L, M1, M2, R, psi = _problem(dtype, chi_l, chi_r, hermitian=True)
+        per_row = 4 * chi_r
+        lo, hi = parallel.row_partition(chi_l, world)[rank]
+        L_rows = parallel.shard_rows(L, 1, rank, world)
+        assert L_rows.shape[1] == hi - lo
+        op = parallel.ShardedApplyMPO(chi_l, per_row, local_op=lambda v, *a, out=None: orc.apply_mpo(v, *a, out=out))
+        # 1. sharded matvec == rows of the full matvec
+        full_ref = orc.apply_mpo(psi, L, M1, M2, R)
+        shard_in = psi[lo * per_row: hi * per_row].clone()
+        out = op(shard_in, L_rows, M1, M2, R)
+        err_mv = float(torch.linalg.norm(out - full_ref[lo * per_row: hi * per_row]) / torch.linalg.norm(full_ref))
+        gathered = parallel.gather_rows(out, chi_l, per_row)
+        err_gather = float(torch.linalg.norm(gathered - full_ref) / torch.linalg.norm(full_ref))
+        # 2. sharded Lanczos == unsharded oracle Lanczos
+        _, E_ref = orc.lanczos_ground_state(psi, orc.apply_mpo, (L, M1, M2, R), num_restarts=2, krylov_dim=4)
+        v_sh, E = parallel.lanczos_ground_state_sharded(shard_in, op, (L_rows, M1, M2, R), num_restarts=2,
+                                                        krylov_dim=4, _vector_ops=TorchVectorOps())
+        _, E_pro_ref = orc.lanczos_ground_state(psi, orc.apply_mpo, (L, M1, M2, R), num_restarts=2, krylov_dim=5,
+                                                pro=True, pro_max_reorth=2)
+        _, E_pro = parallel.lanczos_ground_state_sharded(shard_in, op, (L_rows, M1, M2, R), num_restarts=2,
+                                                         krylov_dim=5, pro=True, pro_max_reorth=2,
+                                                         _vector_ops=TorchVectorOps())
+        # the returned shards assemble into a unit vector
+        nrm2 = torch.tensor([float((v_sh.abs() ** 2).sum())], dtype=torch.float64)
+        dist.all_reduce(nrm2)
+        result_q.put((rank, err_mv, err_gather, E, E_ref, E_pro, E_pro_ref, float(nrm2)))
+    except Exception as ex:      # fail fast in the parent instead of a queue timeout
+        import traceback
+        result_q.put(("error", rank, traceback.format_exc()))
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("chi_l,chi_r,dtype_name", [(8, 6, "float64"), (7, 5, "complex128"), (16, 16, "complex128")])
+def test_sharded_matvec_and_lanczos_world2(chi_l, chi_r, dtype_name):
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, chi_l, chi_r, dtype_name, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = []
+    for _ in range(world):
+        item = q.get(timeout=240)
+        if item[0] == "error":
+            for p in procs:
+                p.kill()
+            pytest.fail(f"rank {item[1]} failed:\n{item[2]}")
+        res.append(item)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    Es = []
+    for rank, err_mv, err_gather, E, E_ref, E_pro, E_pro_ref, nrm2 in res:
+        assert err_mv <= 1e-13 and err_gather <= 1e-13
+        assert abs(E - E_ref) <= 1e-10 * abs(E_ref)
+        assert abs(E_pro - E_pro_ref) <= 1e-10 * abs(E_pro_ref)
+        assert abs(nrm2 - 1.0) <= 1e-12
+        Es.append(E)
+    assert Es[0] == Es[1]                      # every rank sees the same Ritz value
+
+
+def test_row_partition():
+    from quantum_simulation_b200.parallel import row_partition
+    assert row_partition(8, 2) == [(0, 4), (4, 8)]
+    assert row_partition(7, 2) == [(0, 4), (4, 7)]
+    assert row_partition(3, 8) == [(0, 1), (1, 2), (2, 3)] + [(3, 3)] * 5
+    assert row_partition(2048, 8)[7] == (1792, 2048)
+    with pytest.raises(ValueError):
+        row_partition(4, 0)

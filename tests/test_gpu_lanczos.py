@@ -138,7 +138,7 @@ def test_vector_kernels_against_torch(dtype, n):
     coef = torch.tensor([[0.3, -0.2], [1.1, 0.4], [-0.7, 0.0]], dtype=torch.float64)
     scal[10:13] = coef.to(DEV)
     w2 = w.clone()
-    ops.lz_axpy_norm(K, 3, n, w2, n, scal, 10, 20, scratch)
+    ops.lz_axpy_norm(K, 3, n, w2, n, scal, 10, 20, 0, scratch)
     cc = torch.complex(coef[:, 0], coef[:, 1]) if dtype.is_complex else coef[:, 0]
     refw = w.cpu().to(torch.complex128) - (cc.to(torch.complex128)[:, None] * K[:3].cpu().to(torch.complex128)).sum(0)
     assert rel_err(w2.to(torch.complex128), refw) <= tol * 10
@@ -147,7 +147,7 @@ def test_vector_kernels_against_torch(dtype, n):
     ops.lz_scale(w2, dst, n, scal, 20)
     assert rel_err(dst.to(torch.complex128), refw / torch.linalg.norm(refw)) <= tol * 10
     y = [0.5, -0.25, 2.0, 0.125]
-    ops.lz_combine(K, 4, n, y, dst, n, scal, 21, scratch)
+    ops.lz_combine(K, 4, n, y, dst, n, scal, 21, 0, scratch)
     refc = (torch.tensor(y, dtype=torch.complex128)[:, None] * K[:4].cpu().to(torch.complex128)).sum(0)
     assert rel_err(dst.to(torch.complex128), refc) <= tol * 10
     assert abs(float(scal[21, 0]) - float(torch.linalg.norm(refc))) <= tol * 10 * max(1.0, float(torch.linalg.norm(refc)))
