@@ -29,6 +29,7 @@ import torch.nn as nn
 from . import _lib
 from .eigensolver import lanczos_ground_state
 from .mps import MPS
+from .svd import two_site_split
 
 __all__ = ["ApplyMPO", "LeftEnvUpdate", "RightEnvUpdate", "EnvironmentManager", "Sweeps", "DMRG",
            "set_contract_backend"]
@@ -286,15 +287,8 @@ class DMRG(nn.Module):
                 psi_flat = psi_flat + noise_vec * noise
                 psi_flat.div_(torch.linalg.norm(psi_flat))
 
-            # 4. SVD + truncation + MPS update (dmrg.py:684-711)
-            U, S, Vh = torch.linalg.svd(psi_flat.view(chil * d, d * chir), full_matrices=False)
-            keep_max = min(S.numel(), chi)
-            keep_cut = S.numel()
-            if cutoff > 0.0:
-                S2 = S ** 2
-                csum = torch.cumsum(S2 / torch.sum(S2), dim=0)
-                keep_cut = int(torch.searchsorted(csum, 1.0 - cutoff, right=True)) + 1
-            keep = max(1, min(keep_max, keep_cut))
+            # 4. SVD + truncation + MPS update (dmrg.py:684-711); large blocks go through the Gram/eigh split (svd.py)
+            Uk, S, Vhk, keep = two_site_split(psi_flat.view(chil * d, d * chir), chi, cutoff)
             self.history["discarded_weights"].append(torch.sum(S[keep:] ** 2).real.item())
             self.history["bond_dims"].append(int(keep))
             self.history["sweeps"].append(int(sweep_idx))
@@ -302,9 +296,9 @@ class DMRG(nn.Module):
             self.history["sites"].append(int(p))
             sv = S[:keep]
             denom = sv.norm().add_(torch.finfo(sv.dtype).eps)
-            A[p] = nn.Parameter(U[:, :keep].view(chil, d, keep), requires_grad=False)
+            A[p] = nn.Parameter(Uk.reshape(chil, d, keep), requires_grad=False)
             sWeight[p + 1] = nn.Parameter(sv.div(denom), requires_grad=False)
-            B[p + 1] = nn.Parameter(Vh[:keep, :].view(keep, d, chir), requires_grad=False)
+            B[p + 1] = nn.Parameter(Vhk.reshape(keep, d, chir), requires_grad=False)
 
             # 5. environment update (dmrg.py:713-717)
             if direction == "right":

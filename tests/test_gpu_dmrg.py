@@ -61,3 +61,47 @@ def test_notebook_energy_printout_format(capsys):
     assert "Initializing MPS as a right-canonical random state..." in out
     assert "[DMRG] Contraction backend resolved to" in out
     assert "Sweep: 1 of 1, Energy: -2.3275" in out and "Bond dim:" in out
+
+
+# ----------------------------------------------------------------------------- two-site split ("next" row f.1)
+@pytest.mark.parametrize("dtype", [torch.float64, torch.complex128])
+@pytest.mark.parametrize("shape", [(512, 512), (384, 640), (640, 384)])
+def test_two_site_split_gram_path(dtype, shape):
+    """The Gram/eigh split used for large blocks: isometric factors, the reference's truncation rule, the same
+    kept subspace and spectrum as torch.linalg.svd."""
+    from quantum_simulation_b200.svd import two_site_split
+    m, n = shape
+    g = torch.Generator().manual_seed(3)
+    r = min(m, n)
+    U0, _ = torch.linalg.qr(torch.randn(m, r, dtype=dtype, generator=g))
+    V0, _ = torch.linalg.qr(torch.randn(n, r, dtype=dtype, generator=g))
+    s = torch.exp(-torch.arange(r, dtype=torch.float64) * 0.05)
+    theta = ((U0 * s.to(dtype)) @ V0.conj().T).to(DEV)
+    for maxdim, cutoff in ((200, 0.0), (10 ** 6, 1e-10)):
+        U, S, Vh, keep = two_site_split(theta, maxdim, cutoff)
+        Ue, Se, Vhe = torch.linalg.svd(theta, full_matrices=False)
+        S2 = Se ** 2
+        keep_ref = min(r, maxdim)
+        if cutoff > 0:
+            cs = torch.cumsum(S2 / S2.sum(), 0)
+            keep_ref = min(keep_ref, int(torch.searchsorted(cs, torch.tensor(1.0 - cutoff, device=DEV, dtype=cs.dtype), right=True)) + 1)
+        assert keep == keep_ref
+        eye = torch.eye(keep, dtype=dtype, device=DEV)
+        assert float(torch.linalg.norm(U.conj().T @ U - eye)) < 1e-12
+        assert float(torch.linalg.norm(Vh @ Vh.conj().T - eye)) < 1e-12
+        assert float(((S[:keep] - Se[:keep]).abs() / Se[:keep]).max()) < 1e-6
+        rec = (U * S[:keep].to(dtype)) @ Vh
+        best = (Ue[:, :keep] * Se[:keep].to(dtype)) @ Vhe[:keep]
+        assert float(torch.linalg.norm(rec - best)) < 1e-7 * float(Se[0])
+
+
+@pytest.mark.parametrize("name", ["cal_heis_L20", "c1_xxz_L20_chi64_c128", "heis_f64_L20_pro", "nb02_tfim_L6"])
+def test_dmrg_with_gram_split_everywhere(name, monkeypatch):
+    """Force the Gram/eigh split for EVERY block size: per-update energies and bond dimensions still match the
+    reference (energy within 1e-10 relative)."""
+    from quantum_simulation_b200 import svd as qsvd
+    monkeypatch.setattr(qsvd, "FAST_MIN", 2)
+    z, E, dm, mps = run_case(name)
+    Eg = z[f"{name}/energies"]
+    assert dm.history["bond_dims"] == [int(x) for x in z[f"{name}/bond_dims"]]
+    assert np.max(np.abs(E - Eg) / np.abs(Eg)) < 1e-10
