@@ -119,9 +119,54 @@ template <bool CPLX, bool KC> struct FragAddr {
     }
 };
 
+// ---- persistent tile schedule: data-parallel waves + a stream-K tail ------------------------------------
+// The tile count is rarely a multiple of the SM count (chi = 2048, 8 GPUs: 128 tiles on 148 SMs), so the last
+// partial wave would idle SMs.  The grid is one persistent CTA per SM.  Tiles [0, T_sk) -- the remainder wave plus
+// one full wave -- are split in k ("stream-K"): their T_sk * ipt k-iterations are divided evenly over the CTAs;
+// the remaining tiles are dealt round-robin, one whole tile per CTA per wave.  A CTA walks its stream-K range from
+// the END backwards, so the piece it shares with the next-lower CTA comes last: the CTA that owns the final
+// k-iteration of a tile ("finisher") adds the partial accumulators its lower-indexed neighbours wrote at the very
+// START of their own walk.  A CTA therefore only ever waits for lower-indexed CTAs (no co-residency assumption),
+// and the partial sums are added in CTA order (deterministic).
+struct Sched {
+    long long u0, seg_end;      // stream-K unit range [u0, seg_end) still to do (units = k-iterations)
+    int ipt;                    // k-iterations per tile
+    int dp_next, dp_waves, G, c, T_sk;
+    __device__ __forceinline__ void init(long long U_sk, int ipt_, int T_sk_, int dp_waves_, int G_, int c_) {
+        ipt = ipt_; T_sk = T_sk_; dp_waves = dp_waves_; G = G_; c = c_; dp_next = 0;
+        u0 = U_sk * c / G; seg_end = U_sk * (c + 1) / G;
+    }
+    // next segment: k-iterations [it0, it1) of tile `tile`
+    __device__ __forceinline__ bool next(int& tile, int& it0, int& it1) {
+        if (seg_end > u0) {
+            tile = (int)((seg_end - 1) / ipt);
+            const long long tb = (long long)tile * ipt;
+            const long long b = u0 > tb ? u0 : tb;
+            it0 = (int)(b - tb); it1 = (int)(seg_end - tb);
+            seg_end = b;
+            return true;
+        }
+        if (dp_next < dp_waves) {
+            tile = T_sk + dp_next * G + c; it0 = 0; it1 = ipt; ++dp_next;
+            return true;
+        }
+        return false;
+    }
+};
+
+struct SkArgs {
+    long long U_sk;             // stream-K units
+    int T_sk, dp_waves, ipt;
+    double* partial;            // [G][kAccPerThread][kTmaThreads]
+    int* flags;                 // [G], flag == epoch when that CTA's partial is ready
+    int epoch;
+};
+constexpr int kAccPerThread = 64;
+
 template <bool CPLX, bool A_KC, bool B_KC>
 __global__ void __launch_bounds__(kTmaThreads, 1)
-gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TArgs g) {
+gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TArgs g,
+                const SkArgs sk) {
     using C = TCfg<CPLX>;
     constexpr int A_BYTES = C::BM * C::BK * C::ES;
     constexpr int B_BYTES = C::BN * C::BK * C::ES;
@@ -129,6 +174,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     constexpr int S = C::STAGES;
     constexpr int MI = C::WM / 8, NJ = C::WN / 8, KS = C::BK / 4;
     constexpr int ACC = CPLX ? 4 : 2;
+    static_assert(MI * NJ * ACC == kAccPerThread, "partial-tile layout");
 
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -140,13 +186,8 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     const int g8 = lane >> 2, t4 = lane & 3;
     const int wm0 = (warp / C::WARPS_N) * C::WM;
     const int wn0 = (warp % C::WARPS_N) * C::WN;
-
-    int tm, tn, z;
-    tile_coords(blockIdx.x, g.tiles_m, g.tiles_n, tm, tn, z);
-    const int m0 = tm * C::BM, n0 = tn * C::BN;
-
+    const int cta = blockIdx.x, G = gridDim.x;
     const int ktiles = (g.K + C::BK - 1) / C::BK;
-    const int iters = ktiles * g.P;
 
     if (tid == 0) {
         tma_prefetch_desc(&mapA);
@@ -157,129 +198,185 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     }
     __syncthreads();
 
+    // ---- producer (thread 0): walks the same segment sequence as the consumers, S-2 stages ahead
     constexpr int KMUL = CPLX ? 2 : 1;       // innermost TMA coordinate is in float64 units
-    auto issue = [&](int j) {                // one thread: fill slot j % S with k-tile j
-        const int p = j / ktiles, k0 = (j - p * ktiles) * C::BK;
-        const int slot = j % S;
+    Sched ps; ps.init(sk.U_sk, sk.ipt, sk.T_sk, sk.dp_waves, G, cta);
+    int p_tile = -1, p_it = 0, p_it1 = 0, p_m0 = 0, p_n0 = 0, p_z = 0;
+    int pj = 0;                              // CTA-local index of the next k-iteration to issue
+    bool p_more = true;
+    auto produce = [&]() {                   // issue one k-iteration (if any is left); thread 0 only
+        if (p_it == p_it1) {
+            if (!p_more || !ps.next(p_tile, p_it, p_it1)) { p_more = false; return; }
+            int tm, tn;
+            tile_coords(p_tile, g.tiles_m, g.tiles_n, tm, tn, p_z);
+            p_m0 = tm * C::BM; p_n0 = tn * C::BN;
+        }
+        const int slot = pj % S;
+        if (pj >= S) mbar_wait_spin(bar_empty + 8 * slot, ((pj / S) + 1) & 1);
+        const int p = p_it / ktiles, k0 = (p_it - p * ktiles) * C::BK;
         const uint32_t sa = sbase + slot * STAGE, sb = sa + A_BYTES, bar = bar_full + 8 * slot;
         mbar_expect_tx(bar, STAGE);
-        if constexpr (A_KC) tma_load_4d(sa, &mapA, bar, k0 * KMUL, m0, g.a_has_p ? p : 0, g.a_has_z ? z : 0);
-        else tma_load_5d(sa, &mapA, bar, 0, k0, m0 / C::RLO, g.a_has_p ? p : 0, g.a_has_z ? z : 0);
-        if constexpr (B_KC) tma_load_4d(sb, &mapB, bar, k0 * KMUL, n0, g.b_has_p ? p : 0, g.b_has_z ? z : 0);
-        else tma_load_5d(sb, &mapB, bar, 0, k0, n0 / C::RLO, g.b_has_p ? p : 0, g.b_has_z ? z : 0);
+        if constexpr (A_KC) tma_load_4d(sa, &mapA, bar, k0 * KMUL, p_m0, g.a_has_p ? p : 0, g.a_has_z ? p_z : 0);
+        else tma_load_5d(sa, &mapA, bar, 0, k0, p_m0 / C::RLO, g.a_has_p ? p : 0, g.a_has_z ? p_z : 0);
+        if constexpr (B_KC) tma_load_4d(sb, &mapB, bar, k0 * KMUL, p_n0, g.b_has_p ? p : 0, g.b_has_z ? p_z : 0);
+        else tma_load_5d(sb, &mapB, bar, 0, k0, p_n0 / C::RLO, g.b_has_p ? p : 0, g.b_has_z ? p_z : 0);
+        ++p_it; ++pj;
     };
-
     if (tid == 0) {
-        for (int j = 0; j < S - 2 && j < iters; ++j) issue(j);
+        for (int j = 0; j < S - 2; ++j) produce();
     }
-
-    double acc[MI][NJ][ACC];
-#pragma unroll
-    for (int i = 0; i < MI; ++i)
-#pragma unroll
-        for (int j = 0; j < NJ; ++j)
-#pragma unroll
-            for (int q = 0; q < ACC; ++q) acc[i][j][q] = 0.0;
 
     FragAddr<CPLX, A_KC> fa; fa.init(wm0, g8, t4);
     FragAddr<CPLX, B_KC> fb; fb.init(wn0, g8, t4);
 
-    for (int it = 0; it < iters; ++it) {
-        if (tid == 0) {
-            const int j = it + S - 2;
-            if (j < iters) {
-                if (j >= S) mbar_wait_spin(bar_empty + 8 * (j % S), ((j / S) + 1) & 1);
-                issue(j);
-            }
-        }
-        const int slot = it % S;
-        mbar_wait_spin(bar_full + 8 * slot, (it / S) & 1);
-        const unsigned char* sa = smem + slot * STAGE;
-        const unsigned char* sb = sa + A_BYTES;
-        if constexpr (!CPLX) {
-            double a[2][MI], b[2][NJ];
-#pragma unroll
-            for (int i = 0; i < MI; ++i) a[0][i] = *reinterpret_cast<const double*>(sa + fa.at(i, 0));
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) b[0][j] = *reinterpret_cast<const double*>(sb + fb.at(j, 0));
-#pragma unroll
-            for (int kk = 0; kk < KS; ++kk) {
-                const int cur = kk & 1, nxt = cur ^ 1;
-                if (kk + 1 < KS) {
-#pragma unroll
-                    for (int i = 0; i < MI; ++i) a[nxt][i] = *reinterpret_cast<const double*>(sa + fa.at(i, kk + 1));
-#pragma unroll
-                    for (int j = 0; j < NJ; ++j) b[nxt][j] = *reinterpret_cast<const double*>(sb + fb.at(j, kk + 1));
-                }
-#pragma unroll
-                for (int i = 0; i < MI; ++i)
-#pragma unroll
-                    for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[cur][i], b[cur][j]);
-            }
-        } else {
-            double2 a[2][MI], b[2][NJ];
-#pragma unroll
-            for (int i = 0; i < MI; ++i) a[0][i] = *reinterpret_cast<const double2*>(sa + fa.at(i, 0));
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) b[0][j] = *reinterpret_cast<const double2*>(sb + fb.at(j, 0));
-#pragma unroll
-            for (int kk = 0; kk < KS; ++kk) {
-                const int cur = kk & 1, nxt = cur ^ 1;
-                if (kk + 1 < KS) {
-#pragma unroll
-                    for (int i = 0; i < MI; ++i) a[nxt][i] = *reinterpret_cast<const double2*>(sa + fa.at(i, kk + 1));
-#pragma unroll
-                    for (int j = 0; j < NJ; ++j) b[nxt][j] = *reinterpret_cast<const double2*>(sb + fb.at(j, kk + 1));
-                }
-                double ai[MI], nai[MI], bi[NJ];
-#pragma unroll
-                for (int i = 0; i < MI; ++i) { ai[i] = a[cur][i].y * g.sgnA; nai[i] = -ai[i]; }
-#pragma unroll
-                for (int j = 0; j < NJ; ++j) bi[j] = b[cur][j].y * g.sgnB;
-#pragma unroll
-                for (int i = 0; i < MI; ++i)
-#pragma unroll
-                    for (int j = 0; j < NJ; ++j) {
-                        dmma884(acc[i][j][0], acc[i][j][1], a[cur][i].x, b[cur][j].x);
-                        dmma884(acc[i][j][2], acc[i][j][3], a[cur][i].x, bi[j]);
-                    }
-#pragma unroll
-                for (int i = 0; i < MI; ++i)
-#pragma unroll
-                    for (int j = 0; j < NJ; ++j) {
-                        dmma884(acc[i][j][0], acc[i][j][1], nai[i], bi[j]);
-                        dmma884(acc[i][j][2], acc[i][j][3], ai[i], b[cur][j].x);
-                    }
-            }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_empty + 8 * slot);
-    }
+    Sched cs; cs.init(sk.U_sk, sk.ipt, sk.T_sk, sk.dp_waves, G, cta);
+    int tile, it0, it1;
+    int cj = 0;                              // CTA-local index of the k-iteration being consumed
+    double* my_partial = sk.partial + (size_t)cta * kAccPerThread * kTmaThreads + tid;
 
-    // epilogue: lane owns rows frag_index<A>(i, g8) and columns frag_index<B>(j, 2*t4), frag_index<B>(j, 2*t4+1)
-    char* Cz = g.C + g.c_zs * z * C::ES;
-    bool vec_ok = false;
-    if constexpr (!CPLX && !B_KC)        // RC columns come in adjacent pairs -> 16-byte stores
-        vec_ok = (g.c_ns == 1) && ((g.c_ms & 1) == 0) && ((g.c_zs & 1) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15u) == 0);
+    while (cs.next(tile, it0, it1)) {
+        double acc[MI][NJ][ACC];
 #pragma unroll
-    for (int i = 0; i < MI; ++i) {
-        const int m = m0 + wm0 + frag_index<CPLX, A_KC>(i, g8);
-        if (m >= g.M) continue;
+        for (int i = 0; i < MI; ++i)
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-            const int c0 = n0 + wn0 + frag_index<CPLX, B_KC>(j, 2 * t4);
-            const int c1 = n0 + wn0 + frag_index<CPLX, B_KC>(j, 2 * t4 + 1);
-            char* row = Cz + g.c_ms * m * C::ES;
+            for (int j = 0; j < NJ; ++j)
+#pragma unroll
+                for (int q = 0; q < ACC; ++q) acc[i][j][q] = 0.0;
+
+        for (int it = it0; it < it1; ++it, ++cj) {
+            if (tid == 0) produce();
+            const int slot = cj % S;
+            mbar_wait_spin(bar_full + 8 * slot, (cj / S) & 1);
+            const unsigned char* sa = smem + slot * STAGE;
+            const unsigned char* sb = sa + A_BYTES;
             if constexpr (!CPLX) {
-                if (vec_ok && c1 < g.N) {        // c1 == c0 + 1 for the RC permutation
-                    *reinterpret_cast<double2*>(row + (long long)c0 * C::ES) = make_double2(acc[i][j][0], acc[i][j][1]);
-                } else {
-                    if (c0 < g.N) *reinterpret_cast<double*>(row + g.c_ns * c0 * C::ES) = acc[i][j][0];
-                    if (c1 < g.N) *reinterpret_cast<double*>(row + g.c_ns * c1 * C::ES) = acc[i][j][1];
+                double a[2][MI], b[2][NJ];
+#pragma unroll
+                for (int i = 0; i < MI; ++i) a[0][i] = *reinterpret_cast<const double*>(sa + fa.at(i, 0));
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) b[0][j] = *reinterpret_cast<const double*>(sb + fb.at(j, 0));
+#pragma unroll
+                for (int kk = 0; kk < KS; ++kk) {
+                    const int cur = kk & 1, nxt = cur ^ 1;
+                    if (kk + 1 < KS) {
+#pragma unroll
+                        for (int i = 0; i < MI; ++i) a[nxt][i] = *reinterpret_cast<const double*>(sa + fa.at(i, kk + 1));
+#pragma unroll
+                        for (int j = 0; j < NJ; ++j) b[nxt][j] = *reinterpret_cast<const double*>(sb + fb.at(j, kk + 1));
+                    }
+#pragma unroll
+                    for (int i = 0; i < MI; ++i)
+#pragma unroll
+                        for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[cur][i], b[cur][j]);
                 }
             } else {
-                if (c0 < g.N) *reinterpret_cast<double2*>(row + g.c_ns * c0 * C::ES) = make_double2(acc[i][j][0], acc[i][j][2]);
-                if (c1 < g.N) *reinterpret_cast<double2*>(row + g.c_ns * c1 * C::ES) = make_double2(acc[i][j][1], acc[i][j][3]);
+                double2 a[2][MI], b[2][NJ];
+#pragma unroll
+                for (int i = 0; i < MI; ++i) a[0][i] = *reinterpret_cast<const double2*>(sa + fa.at(i, 0));
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) b[0][j] = *reinterpret_cast<const double2*>(sb + fb.at(j, 0));
+#pragma unroll
+                for (int kk = 0; kk < KS; ++kk) {
+                    const int cur = kk & 1, nxt = cur ^ 1;
+                    if (kk + 1 < KS) {
+#pragma unroll
+                        for (int i = 0; i < MI; ++i) a[nxt][i] = *reinterpret_cast<const double2*>(sa + fa.at(i, kk + 1));
+#pragma unroll
+                        for (int j = 0; j < NJ; ++j) b[nxt][j] = *reinterpret_cast<const double2*>(sb + fb.at(j, kk + 1));
+                    }
+                    double ai[MI], nai[MI], bi[NJ];
+#pragma unroll
+                    for (int i = 0; i < MI; ++i) { ai[i] = a[cur][i].y * g.sgnA; nai[i] = -ai[i]; }
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) bi[j] = b[cur][j].y * g.sgnB;
+#pragma unroll
+                    for (int i = 0; i < MI; ++i)
+#pragma unroll
+                        for (int j = 0; j < NJ; ++j) {
+                            dmma884(acc[i][j][0], acc[i][j][1], a[cur][i].x, b[cur][j].x);
+                            dmma884(acc[i][j][2], acc[i][j][3], a[cur][i].x, bi[j]);
+                        }
+#pragma unroll
+                    for (int i = 0; i < MI; ++i)
+#pragma unroll
+                        for (int j = 0; j < NJ; ++j) {
+                            dmma884(acc[i][j][0], acc[i][j][1], nai[i], bi[j]);
+                            dmma884(acc[i][j][2], acc[i][j][3], ai[i], b[cur][j].x);
+                        }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_empty + 8 * slot);
+        }
+
+        // ---- segment epilogue
+        if (it1 < sk.ipt) {
+            // contributor: this CTA does not own the tile's last k-iteration -> publish the partial accumulators
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < NJ; ++j)
+#pragma unroll
+                    for (int q = 0; q < ACC; ++q)
+                        __stcg(my_partial + (size_t)((i * NJ + j) * ACC + q) * kTmaThreads, acc[i][j][q]);
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(sk.flags + cta), "r"(sk.epoch) : "memory");
+            }
+            continue;
+        }
+        if (it0 > 0) {
+            // finisher: add the partials of the lower-indexed CTAs that cover k-iterations [0, it0) of this tile
+            const long long tile_begin = (long long)tile * sk.ipt;
+            for (int cc = cta - 1; cc >= 0 && sk.U_sk * (cc + 1) / G > tile_begin; --cc) {
+                if (tid == 0) {
+                    int v;
+                    const long long t0 = clock64();
+                    do {
+                        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(sk.flags + cc) : "memory");
+                        if (v != sk.epoch && clock64() - t0 > 20000000000LL) __trap();
+                    } while (v != sk.epoch);
+                }
+                __syncthreads();
+                const double* src = sk.partial + (size_t)cc * kAccPerThread * kTmaThreads + tid;
+#pragma unroll
+                for (int i = 0; i < MI; ++i)
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j)
+#pragma unroll
+                        for (int q = 0; q < ACC; ++q)
+                            acc[i][j][q] += __ldcg(src + (size_t)((i * NJ + j) * ACC + q) * kTmaThreads);
+            }
+        }
+        // store: lane owns rows frag_index<A>(i, g8) and columns frag_index<B>(j, 2*t4), frag_index<B>(j, 2*t4+1)
+        int tm, tn, z;
+        tile_coords(tile, g.tiles_m, g.tiles_n, tm, tn, z);
+        const int m0 = tm * C::BM, n0 = tn * C::BN;
+        char* Cz = g.C + g.c_zs * z * C::ES;
+        bool vec_ok = false;
+        if constexpr (!CPLX && !B_KC)        // RC columns come in adjacent pairs -> 16-byte stores
+            vec_ok = (g.c_ns == 1) && ((g.c_ms & 1) == 0) && ((g.c_zs & 1) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15u) == 0);
+#pragma unroll
+        for (int i = 0; i < MI; ++i) {
+            const int m = m0 + wm0 + frag_index<CPLX, A_KC>(i, g8);
+            if (m >= g.M) continue;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const int c0 = n0 + wn0 + frag_index<CPLX, B_KC>(j, 2 * t4);
+                const int c1 = n0 + wn0 + frag_index<CPLX, B_KC>(j, 2 * t4 + 1);
+                char* row = Cz + g.c_ms * m * C::ES;
+                if constexpr (!CPLX) {
+                    if (vec_ok && c1 < g.N) {        // c1 == c0 + 1 for the RC permutation
+                        *reinterpret_cast<double2*>(row + (long long)c0 * C::ES) = make_double2(acc[i][j][0], acc[i][j][1]);
+                    } else {
+                        if (c0 < g.N) *reinterpret_cast<double*>(row + g.c_ns * c0 * C::ES) = acc[i][j][0];
+                        if (c1 < g.N) *reinterpret_cast<double*>(row + g.c_ns * c1 * C::ES) = acc[i][j][1];
+                    }
+                } else {
+                    if (c0 < g.N) *reinterpret_cast<double2*>(row + g.c_ns * c0 * C::ES) = make_double2(acc[i][j][0], acc[i][j][2]);
+                    if (c1 < g.N) *reinterpret_cast<double2*>(row + g.c_ns * c1 * C::ES) = make_double2(acc[i][j][1], acc[i][j][3]);
+                }
             }
         }
     }
@@ -359,6 +456,29 @@ static bool make_map(CUtensorMap* map, const Operand& o, bool cplx, bool kc, int
     return r == CUDA_SUCCESS;
 }
 
+// stream-K scratch, one per device, owned by the library (kernels of one device must not run concurrently on
+// several streams; the DMRG loop is single-stream like the reference)
+struct SkScratch { double* partial = nullptr; int* flags = nullptr; int sms = 0; int epoch = 0; };
+static SkScratch g_sk[16];
+
+static int sk_scratch(SkScratch** out) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return QSB_ERR_DEVICE;
+    SkScratch& s = g_sk[dev];
+    if (!s.partial) {
+        int rc = check_cuda(cudaDeviceGetAttribute(&s.sms, cudaDevAttrMultiProcessorCount, dev));
+        if (rc) return rc;
+        rc = check_cuda(cudaMalloc(&s.partial, (size_t)s.sms * kAccPerThread * kTmaThreads * sizeof(double)));
+        if (rc) return rc;
+        rc = check_cuda(cudaMalloc(&s.flags, (size_t)s.sms * sizeof(int)));
+        if (rc) return rc;
+        rc = check_cuda(cudaMemset(s.flags, 0, (size_t)s.sms * sizeof(int)));
+        if (rc) return rc;
+    }
+    *out = &s;
+    return QSB_OK;
+}
+
 template <bool CPLX, bool A_KC, bool B_KC>
 static int launch_tma(const CUtensorMap& ma, const CUtensorMap& mb, const TArgs& t, int Z, cudaStream_t stream) {
     using C = TCfg<CPLX>;
@@ -370,9 +490,30 @@ static int launch_tma(const CUtensorMap& ma, const CUtensorMap& mb, const TArgs&
         if (rc) return rc;
         configured = true;
     }
-    const long long blocks = (long long)t.tiles_m * t.tiles_n * Z;
-    if (blocks > 2147483647LL) return QSB_ERR_SHAPE;
-    kern<<<(unsigned)blocks, kTmaThreads, SMEM, stream>>>(ma, mb, t);
+    SkScratch* sc = nullptr;
+    int rc = sk_scratch(&sc);
+    if (rc) return rc;
+    const long long tiles = (long long)t.tiles_m * t.tiles_n * Z;
+    if (tiles > 2147483647LL) return QSB_ERR_SHAPE;
+    const int ipt = ((t.K + C::BK - 1) / C::BK) * t.P;
+    // schedule: one persistent CTA per SM; whole waves data-parallel, the remainder (+ one wave) split in k
+    constexpr int kMinIters = 16;             // do not split below this many k-iterations per CTA
+    int G = sc->sms;
+    SkArgs sk;
+    sk.ipt = ipt;
+    if (tiles < G) {
+        long long by_work = tiles * ipt / kMinIters;
+        if (by_work < tiles) by_work = tiles;
+        if (by_work < G) G = (int)by_work;
+    }
+    const long long full = tiles / G, rem = tiles % G;
+    if (rem == 0) { sk.T_sk = 0; sk.dp_waves = (int)full; }
+    else { sk.dp_waves = (int)(full > 0 ? full - 1 : 0); sk.T_sk = (int)(tiles - (long long)sk.dp_waves * G); }
+    sk.U_sk = (long long)sk.T_sk * ipt;
+    sk.partial = sc->partial; sk.flags = sc->flags;
+    sk.epoch = ++sc->epoch;
+    if (sc->epoch == 0x7fffffff) sc->epoch = 0;
+    kern<<<(unsigned)G, kTmaThreads, SMEM, stream>>>(ma, mb, t, sk);
     ++g_count_tma;
     return check_launch();
 }
