@@ -38,6 +38,7 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+NCU_TRAFFIC_STEP1_BYTES = 1.856138e9 + 675.188224e6     # ncu --set full, round 1, chi=2048 f64 step-1 GEMM
 METRIC = "H_eff matvec throughput (DMRG two-site, Heisenberg L=100 bulk bond)"
 UNIT = "GFLOP/s"
 
@@ -286,7 +287,10 @@ def run_ours(args):
     achieved = g1_flops / (g1_ms * 1e-3) / 1e12
     roofline = {"bound": "tensor", "kernel": "gemm (FP64 DMMA), H_eff step 1", "achieved": achieved,
                 "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
-                "traffic": None,
+                "traffic": NCU_TRAFFIC_STEP1_BYTES if (chi == 2048 and world == 1 and dtype == torch.float64) else None,
+                "traffic_source": "profiles/r01_gemm_tma_streamk_ncu_full.md (dram__bytes_read.sum + "
+                                  "dram__bytes_write.sum of one launch; algorithmic 0.97 GB; DRAM at 3-5 % of peak, "
+                                  "the kernel is tensor-bound)",
                 "peak_source": "measured in this run: register-resident mma.sync.m8n8k4.f64 issue-rate probe "
                                "(qsb_probe_dmma); MEASURED_PEAKS.json has no FP64 entry",
                 "algorithmic_flops_per_launch": g1_flops, "avg_launch_ms": g1_ms,
@@ -400,6 +404,39 @@ def extras(args, qsb, _lib, dev, dtype, L, M1, M2, R, theta, peak_tf):
     out["env_update"] = {"ms": s * 1e3, "gflops": ef / s / 1e9, "frac_of_fp64_tensor_peak": ef / s / 1e12 / peak_tf}
     del A
     torch.cuda.empty_cache()
+    # (3b) one full bulk bond step of a sweep at this chi: Lanczos (8 matvecs) + env update + theta build + split
+    try:
+        from quantum_simulation_b200.svd import two_site_split
+        d = M1.shape[2]
+        Ls = Lsq + Lsq.conj().transpose(1, 2)
+        Rs = R + R.conj().transpose(1, 2)
+        A = torch.randn(chi, d, chi, dtype=dtype, device=dev) / chi ** 0.5
+
+        def timed(fn, reps=2):
+            fn()
+            torch.cuda.synchronize()
+            best = 1e30
+            for _ in range(reps):
+                t0 = time.perf_counter()
+                fn()
+                torch.cuda.synchronize()
+                best = min(best, time.perf_counter() - t0)
+            return best
+        t_l = timed(lambda: qsb.lanczos_ground_state(theta, op, (Ls, M1, M2, Rs), num_restarts=2, krylov_dim=4))
+        t_e = timed(lambda: up(Ls, M1, A))
+        t_t = timed(lambda: torch.matmul(A.reshape(chi * d, chi), A.reshape(chi, d * chi)))
+        th = theta.view(chi * d, d * chi)
+        t_s = timed(lambda: two_site_split(th, chi, 0.0))
+        step = t_l + t_e + t_t + t_s
+        out["bond_step"] = {"lanczos_8_matvecs_ms": t_l * 1e3, "env_update_ms": t_e * 1e3, "theta_build_ms": t_t * 1e3,
+                            "two_site_split_ms": t_s * 1e3, "total_ms": step * 1e3,
+                            "sweep_estimate_s": 2 * (100 - 1) * step,
+                            "note": "bulk bond of Heisenberg L=100 at full chi; a sweep is 198 such steps (edge bonds "
+                                    "are cheaper), so sweep_estimate_s is an upper estimate of the sweep time"}
+        del A, Ls, Rs
+        torch.cuda.empty_cache()
+    except Exception as ex:
+        out["bond_step"] = {"error": repr(ex)[:200]}
     # (4) CPU baseline: the oracle on the host cores, bounded sample of the same workload
     cores = os.cpu_count() or 1
     try:

@@ -72,6 +72,16 @@ def case_c1():
 def case_c2():
     """BASELINE config 2: TFIM L=100, chi=512, 10 sweeps on the GPU; 1 oracle sweep on the CPU for the ratio."""
     key, dt = "tfim_c128_L100_g0.5", torch.complex128
+    if "--first-sweep" in sys.argv:         # per-update energies of sweep 1, both two-site-split paths
+        from quantum_simulation_b200 import svd as qsvd
+        out = []
+        for fm, tag in ((256, "gram"), (10 ** 9, "torchsvd")):
+            qsvd.FAST_MIN = fm
+            Eg, tg, dm = run_gpu(key, 100, 512, dt, 1)
+            np.save(os.path.join(ROOT, "gpurun_out", f"c2_first_sweep_{tag}.npy"), Eg)
+            out.append({"case": f"C2 first sweep ({tag})", "gpu_s": tg, "E_end": float(Eg[-1])})
+        qsvd.FAST_MIN = 256
+        return out
     Eg, tg, dm = run_gpu(key, 100, 512, dt, 10)
     res = {"case": "C2 TFIM L=100 g=0.5 chi=512, 10 sweeps", "mpo": key, "gpu_s": tg, "gpu_s_per_sweep": tg / 10,
            "E_final_gpu": float(Eg[-1]), "bond_dim_mid": dm.history["bond_dims"][-50],
