@@ -94,11 +94,17 @@ typedef struct {
     int W_in, W_out;        /* MPO bond on the old-env side / new-env side */
     int d;                  /* physical dimension */
     int chi_in, chi_out;    /* MPS bond on the old-env side / new-env side */
-    const void* env;  int64_t env_stride[3];    /* (W_in, chi_in, chi_in) */
+    const void* env;  int64_t env_stride[3];    /* left : (W_in, chi_bra or chi_in, chi_in); right: (W_in, chi_in, chi_in) */
     const void* M;                              /* left : (W_in, W_out, d, d); right: (W_out, W_in, d, d) */
     const void* site; int64_t site_stride[3];   /* left : A (chi_in, d, chi_out); right: B (chi_out, d, chi_in) */
-    void*       out;                            /* (W_out, chi_out, chi_out) contiguous */
+    void*       out;                            /* left : (W_out, chi_out, chi_out); right: (W_out, chi_bra or chi_out, chi_out); contiguous */
     void*       workspace; size_t workspace_bytes;
+    /* Row-block form used by the multi-GPU sharding over the bra index (chi_bra == 0: plain update).
+       left : env holds only rows [lo, lo+chi_bra) of its bra index and site_bra = A[lo:lo+chi_bra] -> out is this
+              rank's PARTIAL SUM of the full new environment (reduce-scatter across ranks follows);
+       right: site_bra = B[lo:lo+chi_bra] -> out holds rows [lo, lo+chi_bra) of the new environment. */
+    int chi_bra;
+    const void* site_bra; int64_t site_bra_stride[3];
 } qsb_env_desc;
 
 int qsb_env_workspace_bytes(const qsb_env_desc* d, size_t* bytes);

@@ -59,6 +59,8 @@ class EnvDesc(C.Structure):
         ("site", C.c_void_p), ("site_stride", C.c_int64 * 3),
         ("out", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("chi_bra", C.c_int),
+        ("site_bra", C.c_void_p), ("site_bra_stride", C.c_int64 * 3),
     ]
 
 
@@ -242,13 +244,12 @@ def _impl_heff_apply(psi, L, M1, M2, R, out) -> None:
 
 
 def env_desc(env: torch.Tensor, M: torch.Tensor, site: torch.Tensor, out: Optional[torch.Tensor],
-             left: bool) -> EnvDesc:
+             left: bool, site_bra: Optional[torch.Tensor] = None) -> EnvDesc:
     if env.dim() != 3 or M.dim() != 4 or site.dim() != 3:
         raise AssertionError("[EnvUpdate] expected env rank 3, M rank 4, site tensor rank 3")
     d = EnvDesc()
     d.dtype = dtype_code(env.dtype)
     W_in, chi_a, chi_b = env.shape
-    assert chi_a == chi_b, "environment must be square in its two MPS bonds"
     if left:
         Wi, Wo, d1, d2 = M.shape
         ci, ds, co = site.shape
@@ -257,7 +258,21 @@ def env_desc(env: torch.Tensor, M: torch.Tensor, site: torch.Tensor, out: Option
         co, ds, ci = site.shape
     assert Wi == W_in, "Mismatch between environment and MPO bond dimension"
     assert d1 == d2 == ds, "Mismatch in physical dimension"
-    assert ci == chi_a, "Mismatch between environment and MPS bond dimension"
+    assert ci == chi_b, "Mismatch between environment and MPS bond dimension"
+    if site_bra is None:
+        assert chi_a == chi_b, "environment must be square in its two MPS bonds"
+        d.chi_bra = 0
+        d.site_bra = None
+    else:                       # row-block form (multi-GPU sharding over the bra index)
+        rows, ds2, cx = site_bra.shape
+        assert ds2 == ds and cx == (co if left else ci), "site_bra does not match the site tensor"
+        if left:
+            assert chi_a == rows, "left row-block update: env rows must match site_bra rows"
+        else:
+            assert chi_a == chi_b, "right update needs the full (square) old environment"
+        d.chi_bra = rows
+        d.site_bra = site_bra.data_ptr()
+        d.site_bra_stride = (C.c_int64 * 3)(*site_bra.stride())
     d.W_in, d.W_out, d.d, d.chi_in, d.chi_out = W_in, Wo, ds, ci, co
     d.env = env.data_ptr()
     d.env_stride = (C.c_int64 * 3)(*env.stride())
@@ -272,10 +287,10 @@ def env_flops(env, M, site, left: bool) -> float:
     return float(load().qsb_env_flops(C.byref(env_desc(env, M, site, None, left))))
 
 
-def _impl_env(env, M, site, out, left: bool) -> None:
+def _impl_env(env, M, site, out, left: bool, site_bra=None) -> None:
     lib = load()
     dev = _require_cuda(env, M, site, out)
-    d = env_desc(env, M, site, out, left)
+    d = env_desc(env, M, site, out, left, site_bra)
     nb = C.c_size_t(0)
     check(lib.qsb_env_workspace_bytes(C.byref(d), C.byref(nb)), "EnvUpdate")
     ws = workspace(dev, nb.value)
@@ -292,6 +307,14 @@ def _impl_env_left(env, M, site, out) -> None:
 
 def _impl_env_right(env, M, site, out) -> None:
     _impl_env(env, M, site, out, False)
+
+
+def _impl_env_left_rows(env, M, site, site_bra, out) -> None:
+    _impl_env(env, M, site, out, True, site_bra)
+
+
+def _impl_env_right_rows(env, M, site, site_bra, out) -> None:
+    _impl_env(env, M, site, out, False, site_bra)
 
 
 def _impl_lz_dot(X, m: int, ldx: int, w, n: int, scal, out_idx: int, flags: int, scratch) -> None:
@@ -400,6 +423,8 @@ def register_ops() -> None:
     tl.define("heff_apply(Tensor psi, Tensor L, Tensor M1, Tensor M2, Tensor R, Tensor(a!) out) -> ()")
     tl.define("env_left(Tensor env, Tensor M, Tensor site, Tensor(a!) out) -> ()")
     tl.define("env_right(Tensor env, Tensor M, Tensor site, Tensor(a!) out) -> ()")
+    tl.define("env_left_rows(Tensor env, Tensor M, Tensor site, Tensor site_bra, Tensor(a!) out) -> ()")
+    tl.define("env_right_rows(Tensor env, Tensor M, Tensor site, Tensor site_bra, Tensor(a!) out) -> ()")
     tl.define("lz_dot(Tensor X, int m, int ldx, Tensor w, int n, Tensor(a!) scal, int out_idx, int flags, "
               "Tensor(b!) scratch) -> ()")
     tl.define("lz_axpy_norm(Tensor X, int m, int ldx, Tensor(a!) w, int n, Tensor(b!) scal, int coef_idx, "
@@ -410,6 +435,8 @@ def register_ops() -> None:
     tl.impl("heff_apply", _impl_heff_apply, "CUDA")
     tl.impl("env_left", _impl_env_left, "CUDA")
     tl.impl("env_right", _impl_env_right, "CUDA")
+    tl.impl("env_left_rows", _impl_env_left_rows, "CUDA")
+    tl.impl("env_right_rows", _impl_env_right_rows, "CUDA")
     tl.impl("lz_dot", _impl_lz_dot, "CUDA")
     tl.impl("lz_axpy_norm", _impl_lz_axpy_norm, "CUDA")
     tl.impl("lz_scale", _impl_lz_scale, "CUDA")

@@ -420,16 +420,19 @@ extern "C" int qsb_heff_set_stage_events(void* const* events, int count) {
 namespace qsb {
 
 struct EnvLayout {
-    size_t bytes, off_T1, off_T2, off_plan, off_site, off_env;
+    size_t bytes, off_T1, off_T2, off_plan, off_site, off_bra, off_env;
     Plan plan;
-    bool copySite, copyEnv;
+    bool copySite, copyBra, copyEnv, hasBra;
     int R, C;
+    long long cb;            // bra extent: rows of the old env that are contracted (left) / output rows (right)
 };
 
 static int env_check(const qsb_env_desc* d) {
     if (!d) return QSB_ERR_ARG;
     if (d->dtype != QSB_F64 && d->dtype != QSB_C128) return QSB_ERR_DTYPE;
     if (d->W_in < 1 || d->W_out < 1 || d->d < 1 || d->chi_in < 1 || d->chi_out < 1) return QSB_ERR_SHAPE;
+    if (d->chi_bra < 0) return QSB_ERR_SHAPE;
+    if (d->chi_bra > 0 && !d->site_bra) return QSB_ERR_ARG;
     return QSB_OK;
 }
 
@@ -439,16 +442,24 @@ static EnvLayout env_layout(const qsb_env_desc* d, bool left) {
     e.R = d->W_out * d->d;
     e.C = d->W_in * d->d;
     e.plan = plan_layout(e.R, e.C, (int)es);
+    e.hasBra = d->chi_bra > 0;
+    e.cb = e.hasBra ? d->chi_bra : (left ? d->chi_in : d->chi_out);
     const int64_t sdims[3] = {left ? d->chi_in : d->chi_out, d->d, left ? d->chi_out : d->chi_in};
     e.copySite = !is_contig3(sdims, d->site_stride);
-    e.copyEnv = !gemm_ready(d->chi_in, d->chi_in, d->env_stride[1], d->env_stride[2]);
-    const size_t slab = (size_t)d->chi_in * d->d * d->chi_out;
+    const int64_t bdims[3] = {e.cb, d->d, left ? d->chi_out : d->chi_in};
+    e.copyBra = e.hasBra && !is_contig3(bdims, d->site_bra_stride);
+    // left: env is (W_in, cb, chi_in); right: env is (W_in, chi_in, chi_in)
+    e.copyEnv = !gemm_ready(left ? e.cb : d->chi_in, d->chi_in, d->env_stride[1], d->env_stride[2]);
+    const size_t site_elems = (size_t)d->chi_in * d->d * d->chi_out;
+    // intermediates: left T[w][a_ket (chi_in)][s][c' (chi_out)], right T[w][a' (cb)][s][b (chi_in)]
+    const size_t slab = left ? site_elems : (size_t)e.cb * d->d * d->chi_in;
     size_t o = 0;
     e.off_T1 = o;   o = align_up(o + (size_t)d->W_in * slab * es, 256);
     e.off_T2 = o;   o = align_up(o + (size_t)d->W_out * slab * es, 256);
     e.off_plan = o; o += e.plan.bytes;
-    e.off_site = o; if (e.copySite) o = align_up(o + slab * es, 256);
-    e.off_env = o;  if (e.copyEnv) o = align_up(o + (size_t)d->W_in * d->chi_in * d->chi_in * es, 256);
+    e.off_site = o; if (e.copySite) o = align_up(o + site_elems * es, 256);
+    e.off_bra = o;  if (e.copyBra) o = align_up(o + (size_t)e.cb * d->d * (left ? d->chi_out : d->chi_in) * es, 256);
+    e.off_env = o;  if (e.copyEnv) o = align_up(o + (size_t)d->W_in * (left ? e.cb : d->chi_in) * d->chi_in * es, 256);
     e.bytes = o;
     return e;
 }
@@ -464,8 +475,8 @@ static int env_update(const qsb_env_desc* d, bool left, cudaStream_t stream) {
     char* T1 = ws + e.off_T1;
     char* T2 = ws + e.off_T2;
     const PlanPtrs pp = plan_ptrs(ws + e.off_plan, e.plan);
-    const long long ci = d->chi_in, co = d->chi_out, dd = d->d;
-    const long long slab = ci * dd * co;
+    const long long ci = d->chi_in, co = d->chi_out, dd = d->d, cb = e.cb;
+    const long long slab = left ? ci * dd * co : cb * dd * ci;
 
     const void* site = d->site;
     if (e.copySite) {
@@ -473,11 +484,17 @@ static int env_update(const qsb_env_desc* d, bool left, cudaStream_t stream) {
         if ((rc = launch_copy3(cplx, dims, d->site, d->site_stride, ws + e.off_site, 0, stream))) return rc;
         site = ws + e.off_site;
     }
+    const void* bra = e.hasBra ? d->site_bra : site;      // the conjugated copy of the site tensor (a row block of it)
+    if (e.copyBra) {
+        const int64_t dims[3] = {cb, dd, left ? co : ci};
+        if ((rc = launch_copy3(cplx, dims, d->site_bra, d->site_bra_stride, ws + e.off_bra, 0, stream))) return rc;
+        bra = ws + e.off_bra;
+    }
     const void* env = d->env; long long Es[3] = {d->env_stride[0], d->env_stride[1], d->env_stride[2]};
     if (e.copyEnv) {
-        const int64_t dims[3] = {d->W_in, ci, ci};
+        const int64_t dims[3] = {d->W_in, left ? cb : ci, ci};
         if ((rc = launch_copy3(cplx, dims, d->env, d->env_stride, ws + e.off_env, 0, stream))) return rc;
-        env = ws + e.off_env; Es[0] = ci * ci; Es[1] = ci; Es[2] = 1;
+        env = ws + e.off_env; Es[0] = (left ? cb : ci) * ci; Es[1] = ci; Es[2] = 1;
     }
 
     // mix operator G[(w_out, s), (w_in, s')] = M[w, w', s', s]
@@ -504,10 +521,10 @@ static int env_update(const qsb_env_desc* d, bool left, cudaStream_t stream) {
     g1.cplx = g3.cplx = cplx;
     g1.P = g3.P = 1;
     if (left) {
-        // step 1:  T1[w][a_ket][s' c'] = sum_{a_bra} Lp[w][a_bra][a_ket] conj(A)[a_bra][s' c']
-        g1.Z = d->W_in; g1.M = (int)ci; g1.N = (int)(dd * co); g1.K = (int)ci;
+        // step 1:  T1[w][a_ket][s' c'] = sum_{a_bra in block} Lp[w][a_bra][a_ket] conj(A)[a_bra][s' c']
+        g1.Z = d->W_in; g1.M = (int)ci; g1.N = (int)(dd * co); g1.K = (int)cb;
         g1.A = env; g1.a_rs = Es[2]; g1.a_ks = Es[1]; g1.a_zs = Es[0];
-        g1.B = site; g1.b_rs = 1; g1.b_ks = dd * co; g1.b_zs = 0; g1.conjB = 1;
+        g1.B = bra; g1.b_rs = 1; g1.b_ks = dd * co; g1.b_zs = 0; g1.conjB = 1;
         g1.C = T1; g1.c_ms = dd * co; g1.c_ns = 1; g1.c_zs = slab;
         // mix:  T2[w'][a_ket][s][c'] = sum_{w, s'} M[w,w',s',s] T1[w][a_ket][s'][c']
         ma.o_s1 = co; ma.i_us = dd * co; ma.o_us = dd * co; ma.U = (int)ci; ma.X = (int)co;
@@ -517,18 +534,18 @@ static int env_update(const qsb_env_desc* d, bool left, cudaStream_t stream) {
         g3.B = site; g3.b_rs = 1; g3.b_ks = co; g3.b_zs = 0;
         g3.C = d->out; g3.c_ms = co; g3.c_ns = 1; g3.c_zs = co * co;
     } else {
-        // step 1:  T1[w'][a' s'][b_ket] = sum_{b_bra} conj(B)[a' s'][b_bra] Rn[w'][b_bra][b_ket]
-        g1.Z = d->W_in; g1.M = (int)(co * dd); g1.N = (int)ci; g1.K = (int)ci;
-        g1.A = site; g1.a_rs = ci; g1.a_ks = 1; g1.a_zs = 0; g1.conjA = 1;
+        // step 1:  T1[w'][a' s'][b_ket] = sum_{b_bra} conj(B)[a' s'][b_bra] Rn[w'][b_bra][b_ket]   (a' in block)
+        g1.Z = d->W_in; g1.M = (int)(cb * dd); g1.N = (int)ci; g1.K = (int)ci;
+        g1.A = bra; g1.a_rs = ci; g1.a_ks = 1; g1.a_zs = 0; g1.conjA = 1;
         g1.B = env; g1.b_rs = Es[2]; g1.b_ks = Es[1]; g1.b_zs = Es[0];
         g1.C = T1; g1.c_ms = ci; g1.c_ns = 1; g1.c_zs = slab;
         // mix:  T2[w][a'][s][b_ket] = sum_{w', s'} M[w,w',s',s] T1[w'][a'][s'][b_ket]
-        ma.o_s1 = ci; ma.i_us = dd * ci; ma.o_us = dd * ci; ma.U = (int)co; ma.X = (int)ci;
+        ma.o_s1 = ci; ma.i_us = dd * ci; ma.o_us = dd * ci; ma.U = (int)cb; ma.X = (int)ci;
         // step 3:  out[w][a'][a_ket] = sum_{(s b_ket)} T2[w][a'][(s b_ket)] B[a_ket][(s b_ket)]
-        g3.Z = d->W_out; g3.M = (int)co; g3.N = (int)co; g3.K = (int)(dd * ci);
+        g3.Z = d->W_out; g3.M = (int)cb; g3.N = (int)co; g3.K = (int)(dd * ci);
         g3.A = T2; g3.a_rs = dd * ci; g3.a_ks = 1; g3.a_zs = slab;
         g3.B = site; g3.b_rs = dd * ci; g3.b_ks = 1; g3.b_zs = 0;
-        g3.C = d->out; g3.c_ms = co; g3.c_ns = 1; g3.c_zs = co * co;
+        g3.C = d->out; g3.c_ms = co; g3.c_ns = 1; g3.c_zs = cb * co;
     }
     if ((rc = gemm_launch(g1, stream))) return rc;
     if ((rc = launch_mix(cplx, ma, stream))) return rc;
@@ -554,6 +571,7 @@ extern "C" double qsb_env_flops(const qsb_env_desc* d) {
     if (env_check(d)) return 0.0;
     const double c = d->dtype == QSB_C128 ? 8.0 : 2.0;
     const double W = d->W_in, Wp = d->W_out, dd = d->d, chi = d->chi_in, chip = d->chi_out;
+    if (d->chi_bra > 0) return 0.0;      // row-block calls: count flops on the unsharded descriptor
     return c * (W * dd * chi * chi * chip + W * Wp * dd * dd * chi * chip + Wp * dd * chi * chip * chip);
 }
 

@@ -18,7 +18,8 @@ import torch
 
 from .eigensolver import _lanczos_impl, _CUDA_OPS
 
-__all__ = ["row_partition", "ShardedApplyMPO", "lanczos_ground_state_sharded", "shard_rows", "gather_rows"]
+__all__ = ["row_partition", "ShardedApplyMPO", "lanczos_ground_state_sharded", "shard_rows", "gather_rows",
+           "ShardedDMRG", "CudaEngine"]
 
 
 def row_partition(chi: int, world: int) -> List[Tuple[int, int]]:
@@ -120,3 +121,298 @@ def lanczos_ground_state_sharded(initial_shard: torch.Tensor, linear_operator: C
         raise RuntimeError("qsb200 sharded Lanczos runs on CUDA tensors only (no CPU fallback)")
     return _lanczos_impl(initial_shard, linear_operator, tuple(operator_args), num_restarts, krylov_dim, pro,
                          pro_max_reorth, beta_tol, ritz_residual_tol, group=group, vec=vec)
+
+
+# =====================================================================================================
+# Sharded environments and the sharded two-site DMRG driver
+# =====================================================================================================
+class CudaEngine:
+    """The compute engine of the sharded driver: this package's CUDA kernels.  (The gloo tests of the multi-rank
+    HOST logic inject a CPU engine with the same methods built on the oracle; the product never does.)"""
+
+    def __init__(self):
+        from .dmrg import ApplyMPO, LeftEnvUpdate, RightEnvUpdate
+        from . import _lib
+        self._lib = _lib
+        self.apply_mpo = ApplyMPO()
+        self._left, self._right = LeftEnvUpdate(), RightEnvUpdate()
+        self.vector_ops = None                       # None -> CudaVectorOps
+
+    def env_left(self, Lp, M, A):
+        return self._left(Lp, M, A)
+
+    def env_right(self, M, Rn, B):
+        return self._right(M, Rn, B)
+
+    def env_left_rows(self, Lp_rows, M, A, A_rows):
+        """Partial sum of the full new left environment from the bra-row block this rank owns."""
+        out = torch.empty(M.shape[1], A.shape[2], A.shape[2], device=Lp_rows.device, dtype=Lp_rows.dtype)
+        self._lib.ops.env_left_rows(Lp_rows, M.contiguous(), A, A_rows, out)
+        return out
+
+    def env_right_rows(self, M, Rn, B, B_rows):
+        """Rows [lo, hi) of the new right environment (no communication needed)."""
+        out = torch.empty(M.shape[0], B_rows.shape[0], B.shape[0], device=Rn.device, dtype=Rn.dtype)
+        self._lib.ops.env_right_rows(Rn, M.contiguous(), B, B_rows, out)
+        return out
+
+    def split(self, theta2d, maxdim, cutoff):
+        from .svd import two_site_split
+        return two_site_split(theta2d, maxdim, cutoff)
+
+    def lanczos(self, v, op, args, **kw):
+        from .eigensolver import lanczos_ground_state
+        return lanczos_ground_state(v, op, args, **kw)
+
+
+class _Env:
+    """One cached environment: either replicated (full (W, chi, chi)) or this rank's row block (W, rows, chi)."""
+    __slots__ = ("t", "sharded", "chi")
+
+    def __init__(self, t: torch.Tensor, sharded: bool, chi: int):
+        self.t, self.sharded, self.chi = t, sharded, chi
+
+
+class ShardedDMRG:
+    """Two-site DMRG with the inner loop sharded over the left bond index across the ranks of ``group``.
+
+    Same schedule semantics and ``history`` keys as ``DMRG`` (reference dmrg.py:506-802).  Every rank holds the
+    (small) MPS replicated and runs the same control flow.  What is distributed:
+      * environments ``L[p]`` / ``R[p]`` are stored as row blocks over their bra index whenever the bond is
+        shardable (``chi % world == 0 and chi >= min_shard_chi``), else replicated;
+      * the Lanczos solve runs on row shards (``lanczos_ground_state_sharded`` + ``ShardedApplyMPO``): one
+        all-gather of the vector per matvec, one small all-reduce per scalar;
+      * ``update_L`` contracts the sharded bra index: every rank produces a partial sum of the new environment,
+        combined and re-sharded with one reduce-scatter; ``update_R`` computes its own row block locally;
+      * the right environment of the active bond is all-gathered once per bond step (it multiplies the unsharded
+        right bond of theta);
+      * the two-site split runs on rank 0 and its factors are broadcast, so all ranks hold bit-identical MPS
+        tensors (a replicated cuSOLVER call is not guaranteed to be bit-reproducible across devices).
+    """
+
+    def __init__(self, mps, mpo, *, device, dtype=torch.float64, group=None, min_shard_chi: int = 64, engine=None):
+        import torch.distributed as dist
+        from .dmrg import _as_mpo_list, _check_mpo_shapes
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.device, self.dtype = device, dtype
+        self.mps = mps
+        self.Nsites = len(mpo)
+        self.Ms = _as_mpo_list(list(mpo), self.Nsites, device, dtype)
+        self.chid = self.Ms[0].shape[2]
+        ML = torch.ones(self.Ms[0].shape[0], 1, 1, device=device, dtype=dtype)
+        MR = torch.ones(self.Ms[-1].shape[1], 1, 1, device=device, dtype=dtype)
+        _check_mpo_shapes(self.Ms, ML, MR, self.chid)
+        self.min_shard_chi = int(min_shard_chi)
+        self.engine = engine if engine is not None else CudaEngine()
+        self.history = self._empty_history()
+        self.comm = {"all_gather_vec": 0, "all_gather_env": 0, "reduce_scatter_env": 0, "all_reduce_env": 0,
+                     "broadcast_split": 0, "sharded_steps": 0, "replicated_steps": 0}
+
+    @staticmethod
+    def _empty_history() -> dict:
+        return {"energies": [], "discarded_weights": [], "bond_dims": [], "sweeps": [], "directions": [], "sites": []}
+
+    # ---- sharding policy / conversions ------------------------------------------------------------------
+    def _shardable(self, chi: int) -> bool:
+        return self.world > 1 and chi >= self.min_shard_chi and chi % self.world == 0
+
+    def _block(self, chi: int) -> Tuple[int, int]:
+        return row_partition(chi, self.world)[self.rank]
+
+    def _full(self, e: _Env) -> torch.Tensor:
+        import torch.distributed as dist
+        if not e.sharded:
+            return e.t
+        W, rows, chi = e.t.shape
+        buf = torch.empty(self.world * W * rows * chi, dtype=e.t.dtype, device=e.t.device)
+        dist.all_gather_into_tensor(buf, e.t.contiguous().view(-1), group=self.group)
+        self.comm["all_gather_env"] += 1
+        return buf.view(self.world, W, rows, chi).permute(1, 0, 2, 3).reshape(W, self.world * rows, chi)
+
+    def _rows(self, e: _Env) -> torch.Tensor:
+        if e.sharded:
+            return e.t
+        lo, hi = self._block(e.chi)
+        return e.t[:, lo:hi, :]
+
+    def _store(self, full: torch.Tensor) -> _Env:
+        chi = full.shape[1]
+        if self._shardable(chi):
+            lo, hi = self._block(chi)
+            return _Env(full[:, lo:hi, :].contiguous(), True, chi)
+        return _Env(full, False, chi)
+
+    # ---- environment updates ---------------------------------------------------------------------------
+    def _update_L(self, Lp: _Env, M: torch.Tensor, A: torch.Tensor) -> _Env:
+        import torch.distributed as dist
+        chi_new = A.shape[2]
+        if not Lp.sharded:
+            return self._store(self.engine.env_left(Lp.t, M, A))
+        lo, hi = self._block(Lp.chi)
+        partial = self.engine.env_left_rows(Lp.t, M, A, A[lo:hi])          # (W', chi', chi'), partial sum
+        if self._shardable(chi_new):
+            Wn = partial.shape[0]
+            rows = chi_new // self.world
+            send = partial.permute(1, 0, 2).contiguous()                    # rows outermost for the scatter
+            recv = torch.empty(rows * Wn * chi_new, dtype=partial.dtype, device=partial.device)
+            if dist.get_backend(self.group) == "gloo":    # gloo (CPU tests) has no reduce-scatter: all-reduce + slice
+                flat = send.view(-1)
+                dist.all_reduce(flat, group=self.group)
+                recv.copy_(flat[self.rank * recv.numel(): (self.rank + 1) * recv.numel()])
+            else:
+                dist.reduce_scatter_tensor(recv, send.view(-1), group=self.group)
+            self.comm["reduce_scatter_env"] += 1
+            return _Env(recv.view(rows, Wn, chi_new).permute(1, 0, 2), True, chi_new)   # strided view, last dim contiguous
+        dist.all_reduce(partial, group=self.group)
+        self.comm["all_reduce_env"] += 1
+        return _Env(partial, False, chi_new)
+
+    def _update_R(self, M: torch.Tensor, Rn_full: torch.Tensor, B: torch.Tensor) -> _Env:
+        chi_new = B.shape[0]
+        if self._shardable(chi_new):
+            lo, hi = self._block(chi_new)
+            return _Env(self.engine.env_right_rows(M, Rn_full, B, B[lo:hi]), True, chi_new)
+        return _Env(self.engine.env_right(M, Rn_full, B), False, chi_new)
+
+    # ---- one bond step ----------------------------------------------------------------------------------
+    def _ground_state(self, theta: torch.Tensor, L: _Env, M1, M2, R_full, chi_l: int, kw: dict):
+        per_row = M1.shape[3] * M2.shape[3] * R_full.shape[2]
+        if L.sharded:
+            lo, hi = self._block(chi_l)
+            op = ShardedApplyMPO(chi_l, per_row, group=self.group, local_op=self.engine.apply_mpo)
+            shard = theta.reshape(-1)[lo * per_row: hi * per_row]
+            v, E = lanczos_ground_state_sharded(shard, op, (L.t, M1, M2, R_full), group=self.group,
+                                                _vector_ops=self.engine.vector_ops, **kw)
+            self.comm["all_gather_vec"] += 1 + kw["num_restarts"] * kw["krylov_dim"]
+            self.comm["sharded_steps"] += 1
+            return gather_rows(v, chi_l, per_row, self.group), E
+        self.comm["replicated_steps"] += 1
+        v, E = self.engine.lanczos(theta.reshape(-1), self.engine.apply_mpo, (L.t, M1, M2, R_full), **kw)
+        return v, E
+
+    def _split(self, theta2d: torch.Tensor, chi: int, cutoff: float):
+        """Two-site split on rank 0, factors broadcast to everyone."""
+        import torch.distributed as dist
+        m, n = theta2d.shape
+        src = dist.get_global_rank(self.group, 0)
+        meta = torch.zeros(2, dtype=torch.int64, device=theta2d.device)
+        if self.rank == 0:
+            U, S, Vh, keep = self.engine.split(theta2d, chi, cutoff)
+            meta[0], meta[1] = keep, S.numel()
+        dist.broadcast(meta, src=src, group=self.group)
+        keep, ns = int(meta[0]), int(meta[1])
+        rdt = torch.float64 if theta2d.dtype in (torch.float64, torch.complex128) else torch.float32
+        if self.rank != 0:
+            U = torch.empty(m, keep, dtype=theta2d.dtype, device=theta2d.device)
+            S = torch.empty(ns, dtype=rdt, device=theta2d.device)
+            Vh = torch.empty(keep, n, dtype=theta2d.dtype, device=theta2d.device)
+        else:
+            U, S, Vh = U.contiguous(), S.contiguous(), Vh.contiguous()
+        for t in (U, S, Vh):
+            dist.broadcast(t, src=src, group=self.group)
+        self.comm["broadcast_split"] += 1
+        return U, S, Vh, keep
+
+    def _sweep(self, direction: str, L: list, R: list, params: dict, Ekeep: list) -> None:
+        import torch.nn as nn
+        mps, d, N = self.mps, self.chid, self.Nsites
+        A, B, sW = mps.A, mps.B, mps.sWeight
+        sites = range(N - 1) if direction == "right" else range(N - 2, -1, -1)
+        kw = dict(num_restarts=params["maxit"], krylov_dim=params["krydim"], pro=params["reortho"],
+                  pro_max_reorth=params["maxreortho"])
+        for p in sites:
+            if direction == "right":                                  # theta build, replicated (dmrg.py:633-646)
+                lt, rt, sw = B[p], B[p + 1], sW[p]
+                if sw.dim() == 2:
+                    sw = torch.diagonal(sw, 0)
+                l, s, m = lt.shape
+                _m, t, r = rt.shape
+                psi = torch.matmul(torch.mul(lt, sw.to(lt.dtype).view(-1, 1, 1)).reshape(l * s, m), rt.reshape(m, t * r))
+            else:                                                     # (dmrg.py:647-660)
+                lt, rt, sw = A[p], A[p + 1], sW[p + 2]
+                if sw.dim() == 2:
+                    sw = torch.diagonal(sw, 0)
+                l, s, m = lt.shape
+                _m, t, r = rt.shape
+                psi = torch.matmul(lt.reshape(l * s, m), torch.mul(rt, sw.to(rt.dtype).view(1, 1, -1)).reshape(m, t * r))
+            chil, chir = l, r
+            R_full = self._full(R[p + 2])
+            theta, E = self._ground_state(psi, L[p], self.Ms[p], self.Ms[p + 1], R_full, chil, kw)
+            Ekeep.append(E)
+            self.history["energies"].append(float(E))
+            Uk, S, Vhk, keep = self._split(theta.reshape(chil * d, d * chir), params["chi"], params["cutoff"])
+            self.history["discarded_weights"].append(torch.sum(S[keep:] ** 2).real.item())
+            self.history["bond_dims"].append(int(keep))
+            self.history["sweeps"].append(int(params["sweep_idx"]))
+            self.history["directions"].append(direction)
+            self.history["sites"].append(int(p))
+            sv = S[:keep]
+            denom = sv.norm().add_(torch.finfo(sv.dtype).eps)
+            A[p] = nn.Parameter(Uk.reshape(chil, d, keep), requires_grad=False)
+            sW[p + 1] = nn.Parameter(sv.div(denom), requires_grad=False)
+            B[p + 1] = nn.Parameter(Vhk.reshape(keep, d, chir), requires_grad=False)
+            if direction == "right":
+                L[p + 1] = self._update_L(L[p], self.Ms[p], A[p])
+            else:
+                R[p + 1] = self._update_R(self.Ms[p + 1], R_full, B[p + 1])
+            if params["dispon"] == 2 and self.rank == 0:
+                print(f"Sweep: {params['sweep_idx']} of {params['numsweeps']}, Loc: {p}, Energy: {Ekeep[-1]:.6f}")
+
+    def _boundary(self, mat: torch.Tensor):
+        """Small boundary SVD (dmrg.py:776, 793): rank 0 computes, everyone receives the same factors."""
+        import torch.distributed as dist
+        U, S, Vh = torch.linalg.svd(mat, full_matrices=False)
+        src = dist.get_global_rank(self.group, 0)
+        for t in (U, S, Vh):
+            dist.broadcast(t, src=src, group=self.group)
+        return U, S, Vh
+
+    def forward(self, sweeps, *, dispon=2, updateon=True, maxit=2):
+        import torch.nn as nn
+        if not updateon:
+            raise ValueError("ShardedDMRG always updates (updateon=False is a single-GPU debugging mode)")
+        N, d = self.Nsites, self.chid
+        Ekeep: list = []
+        self.history = self._empty_history()
+        L: list = [None] * (N + 1)
+        R: list = [None] * (N + 1)
+        L[0] = _Env(torch.ones(self.Ms[0].shape[0], 1, 1, device=self.device, dtype=self.dtype), False, 1)
+        R[N] = _Env(torch.ones(self.Ms[-1].shape[1], 1, 1, device=self.device, dtype=self.dtype), False, 1)
+        for p in range(N - 1, self.mps.ortho_center, -1):                          # dmrg.py:752-753
+            R[p] = self._update_R(self.Ms[p], self._full(R[p + 1]), self.mps.B[p])
+        for k in range(1, sweeps.numsweeps + 1):
+            params = {"chi": sweeps.maxdim[k - 1], "krydim": sweeps.krylov_dim[k - 1], "cutoff": sweeps.cutoff[k - 1],
+                      "reortho": sweeps.reortho[k - 1], "maxreortho": sweeps.maxreortho[k - 1], "dispon": dispon,
+                      "maxit": maxit, "sweep_idx": k, "numsweeps": sweeps.numsweeps}
+            if sweeps.noise[k - 1] > 0:
+                raise ValueError("ShardedDMRG does not support noise > 0 (the reference's noise uses the global RNG)")
+            self._sweep("right", L, R, params, Ekeep)
+            self.mps.ortho_center = N - 1
+            sw = self.mps.sWeight[N - 1]                                            # dmrg.py:769-781
+            if sw.dim() == 2:
+                sw = torch.diagonal(sw, 0)
+            Bl = self.mps.B[N - 1]
+            U, S, Vh = self._boundary((sw.to(Bl.dtype).view(-1, 1, 1) * Bl).reshape(Bl.shape[0] * d, Bl.shape[2]))
+            eps = torch.finfo(S.dtype).eps
+            self.mps.A[N - 1] = nn.Parameter(U.view(Bl.shape[0], d, Bl.shape[2]), requires_grad=False)
+            self.mps.sWeight[N] = nn.Parameter((S.unsqueeze(1) * Vh).to(self.dtype) / (S.norm().add_(eps)),
+                                               requires_grad=False)
+            self._sweep("left", L, R, params, Ekeep)
+            self.mps.ortho_center = 0
+            sw = self.mps.sWeight[1]                                                # dmrg.py:787-796
+            if sw.dim() == 2:
+                sw = torch.diagonal(sw, 0)
+            A0 = self.mps.A[0] * sw.to(self.mps.A[0].dtype).view(1, 1, -1)
+            chil, _, chir = self.mps.A[0].shape
+            U, S, Vh = self._boundary(A0.reshape(chil, d * chir))
+            self.mps.B[0] = nn.Parameter(Vh.view(chil, d, chir), requires_grad=False)
+            self.mps.sWeight[0] = nn.Parameter((U * S.unsqueeze(0)).to(self.dtype) / (S.norm().add_(eps)),
+                                               requires_grad=False)
+            if dispon == 1 and self.rank == 0:
+                print(f"Sweep: {k} of {sweeps.numsweeps}, Energy: {Ekeep[-1]:.12f}, "
+                      f"Bond dim: {self.mps.A[N // 2].shape[-1]}")
+        return Ekeep, self.mps
+
+    __call__ = forward

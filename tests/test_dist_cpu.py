@@ -112,6 +112,73 @@ def test_sharded_matvec_and_lanczos_world2(chi_l, chi_r, dtype_name):
     assert Es[0] == Es[1]                      # every rank sees the same Ritz value
 
 
+def _dmrg_worker(rank, world, port, dtype_name, result_q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import io
+        import contextlib
+        torch.set_num_threads(2)
+        import quantum_simulation_b200 as qsb
+        from quantum_simulation_b200 import parallel
+        from oracle import dmrg_oracle as orc
+        from conftest import golden_mpo
+        from engine_cpu import CpuEngine
+        dtype = getattr(torch, dtype_name)
+        mpo = golden_mpo("heis_c128_L20" if dtype.is_complex else "heis_f64_L20", dtype)
+        sched = dict(numsweeps=2, maxdim=[16, 16], krylov_dim=[4, 4], cutoff=[0.0, 1e-12], reortho=[False, True],
+                     maxreortho=[1, 1])
+        ref_mps = orc.OracleMPS(20, 2, 16, dtype, seed=5)
+        E_ref, h_ref = orc.dmrg_run(ref_mps, mpo, **sched)
+        with contextlib.redirect_stdout(io.StringIO()):
+            mps = qsb.MPS(20, 2, 16, "cpu", dtype, seed=5)
+        sw = qsb.Sweeps(2)
+        sw.set_schedule(maxdim=sched["maxdim"], krylov_dim=sched["krylov_dim"], cutoff=sched["cutoff"],
+                        reortho=sched["reortho"], maxreortho=sched["maxreortho"])
+        dm = parallel.ShardedDMRG(mps, mpo, device="cpu", dtype=dtype, min_shard_chi=4, engine=CpuEngine())
+        E, _ = dm(sw, dispon=0)
+        rel = max(abs(a - b) / abs(b) for a, b in zip(E, E_ref))
+        result_q.put((rank, len(E) == len(E_ref), rel, dm.history["bond_dims"] == h_ref["bond_dims"], dict(dm.comm),
+                      float(E[-1])))
+    except Exception:
+        import traceback
+        result_q.put(("error", rank, traceback.format_exc()))
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("dtype_name", ["float64", "complex128"])
+def test_sharded_dmrg_world2_matches_unsharded(dtype_name):
+    """Full two-site DMRG (2 sweeps, Heisenberg L=20, chi=16) through ShardedDMRG on 2 gloo ranks: row-sharded
+    environments, sharded Lanczos, reduce-scatter env updates, broadcast split -- per-update energies equal the
+    unsharded run to 1e-10 relative and every rank ends with the same energy."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_dmrg_worker, args=(r, world, port, dtype_name, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = []
+    for _ in range(world):
+        item = q.get(timeout=600)
+        if item[0] == "error":
+            for p in procs:
+                p.kill()
+            pytest.fail(f"rank {item[1]} failed:\n{item[2]}")
+        res.append(item)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, same_len, rel, same_bonds, comm, E_last in res:
+        assert same_len and same_bonds
+        assert rel <= 1e-10, f"rank {rank}: max relative deviation {rel:.2e}"
+        assert comm["sharded_steps"] > 0 and comm["replicated_steps"] > 0
+        assert comm["reduce_scatter_env"] > 0 and comm["all_gather_env"] > 0 and comm["broadcast_split"] > 0
+    assert res[0][5] == res[1][5]
+
+
 def test_row_partition():
     from quantum_simulation_b200.parallel import row_partition
     assert row_partition(8, 2) == [(0, 4), (4, 8)]

@@ -237,6 +237,34 @@ def test_env_vs_oracle_seeded(dtype, chi, chip):
     assert rel_err(outL, refL) <= TOL and rel_err(outR, refR) <= TOL
 
 
+@pytest.mark.parametrize("dtype", [torch.float64, torch.complex128])
+@pytest.mark.parametrize("chi,chip,lo,hi", [(64, 48, 16, 32), (96, 96, 0, 48), (33, 20, 5, 6)])
+def test_env_row_block_forms(dtype, chi, chip, lo, hi):
+    """Row-block env updates used by the multi-GPU sharding: left = partial sum over a bra-row block (the blocks add
+    up to the full update), right = a row block of the new environment."""
+    mpo = golden_mpo("heis_f64_L100" if dtype == torch.float64 else "heis_c128_L100", dtype)
+    M = mpo[40]
+    W, Wp, d = M.shape[0], M.shape[1], M.shape[2]
+    Lp = randn((W, chi, chi), dtype, 40)
+    A = randn((chi, d, chip), dtype, 41)
+    Rn = randn((Wp, chip, chip), dtype, 42)
+    B = randn((chi, d, chip), dtype, 43)
+    ops = _lib.ops
+    part = torch.empty(Wp, chip, chip, dtype=dtype, device=DEV)
+    Ad = A.to(DEV)
+    ops.env_left_rows(Lp[:, lo:hi, :].to(DEV), M.to(DEV), Ad, Ad[lo:hi], part)
+    ref_part = torch.einsum("wak,apc,wvps,ksd->vcd", Lp[:, lo:hi, :], A[lo:hi].conj(), M, A)
+    assert rel_err(part, ref_part) <= TOL
+    rest = torch.empty_like(part)
+    idx = [i for i in range(chi) if not (lo <= i < hi)]
+    ops.env_left_rows(Lp[:, idx, :].to(DEV), M.to(DEV), Ad, Ad[idx], rest)
+    assert rel_err(part + rest, orc.left_env_update(Lp, M, A)) <= TOL
+    rows = torch.empty(W, hi - lo, chi, dtype=dtype, device=DEV)
+    Bd = B.to(DEV)
+    ops.env_right_rows(Rn.to(DEV), M.to(DEV), Bd, Bd[lo:hi], rows)
+    assert rel_err(rows, orc.right_env_update(M, Rn, B)[:, lo:hi, :]) <= TOL
+
+
 def test_environment_manager_chain_matches_oracle():
     """update_R from the right boundary then update_L from the left one, on a real right-canonical MPS."""
     dtype = torch.complex128

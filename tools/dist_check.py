@@ -27,6 +27,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--chi", type=int, default=512)
     ap.add_argument("--dtype", default="f64")
+    ap.add_argument("--dmrg-chi", type=int, default=64)
     args = ap.parse_args()
     rank, world, local = bench.dist_setup(0)
     dev = torch.device("cuda", local)
@@ -61,14 +62,38 @@ def main():
     qsb.lanczos_ground_state(theta, op1, (L, M1, M2, R), num_restarts=2, krylov_dim=4)
     torch.cuda.synchronize()
     t_1 = time.perf_counter() - t0
-    errs = torch.tensor([err, abs(E - E1) / abs(E1), abs(Ep - E1p) / abs(E1p)], dtype=torch.float64, device=dev)
+    # full sharded DMRG (row-sharded environments, reduce-scatter env updates) vs the single-GPU driver
+    import contextlib, io
+    import numpy as np
+    mkey = "heis_f64_L20" if dtype == torch.float64 else "heis_c128_L20"
+    mpo = [m.to(dev) for m in bench.load_mpo(mkey, dtype)]
+    chi_d = args.dmrg_chi
+
+    def sched():
+        sw = qsb.Sweeps(2)
+        sw.set_schedule(maxdim=[chi_d, chi_d], cutoff=[0.0, 0.0], krylov_dim=[4, 4], noise=[0.0, 0.0])
+        return sw
+    with contextlib.redirect_stdout(io.StringIO()):
+        m1 = qsb.MPS(20, 2, chi_d, "cpu", dtype, seed=3).to(dev)
+        d1 = qsb.DMRG(m1, mpo, device=dev, dtype=dtype)
+        t0 = time.perf_counter(); Es, _ = d1(sched(), dispon=0); torch.cuda.synchronize(); t_single = time.perf_counter() - t0
+        m2 = qsb.MPS(20, 2, chi_d, "cpu", dtype, seed=3).to(dev)
+    d2 = parallel.ShardedDMRG(m2, mpo, device=dev, dtype=dtype, min_shard_chi=16)
+    dist.barrier()
+    t0 = time.perf_counter(); Ed, _ = d2(sched(), dispon=0); torch.cuda.synchronize(); t_shard = time.perf_counter() - t0
+    dmrg_dev = float(np.max(np.abs(np.array(Ed) - np.array(Es)) / np.abs(np.array(Es))))
+    bonds_ok = d2.history["bond_dims"] == d1.history["bond_dims"]
+    errs = torch.tensor([err, abs(E - E1) / abs(E1), abs(Ep - E1p) / abs(E1p), dmrg_dev, 0.0 if bonds_ok else 1.0],
+                        dtype=torch.float64, device=dev)
     dist.all_reduce(errs, op=dist.ReduceOp.MAX)
-    ok = bool(errs[0] <= 1e-12 and errs[1] <= 1e-10 and errs[2] <= 1e-10)
+    ok = bool(errs[0] <= 1e-12 and errs[1] <= 1e-10 and errs[2] <= 1e-10 and errs[3] <= 1e-10 and errs[4] == 0.0)
     if rank == 0:
         print(json.dumps({"world": world, "chi": chi, "dtype": args.dtype, "matvec_rel_err": float(errs[0]),
                           "lanczos_rel_dev": float(errs[1]), "lanczos_pro_rel_dev": float(errs[2]),
                           "E_sharded": E, "E_single": E1, "lanczos_solve_s_sharded": t_sh,
-                          "lanczos_solve_s_single_gpu": t_1, "ok": ok}))
+                          "lanczos_solve_s_single_gpu": t_1, "dmrg_L20_chi": chi_d,
+                          "dmrg_max_rel_dev_per_update": float(errs[3]), "dmrg_bond_dims_equal": bool(errs[4] == 0.0),
+                          "dmrg_s_single": t_single, "dmrg_s_sharded": t_shard, "dmrg_comm": d2.comm, "ok": ok}))
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
 
