@@ -309,7 +309,7 @@ class ShardedDMRG:
             S = torch.empty(ns, dtype=rdt, device=theta2d.device)
             Vh = torch.empty(keep, n, dtype=theta2d.dtype, device=theta2d.device)
         else:
-            U, S, Vh = U.contiguous(), S.contiguous(), Vh.contiguous()
+            U, S, Vh = U.resolve_conj().contiguous(), S.contiguous(), Vh.resolve_conj().contiguous()
         for t in (U, S, Vh):
             dist.broadcast(t, src=src, group=self.group)
         self.comm["broadcast_split"] += 1
@@ -364,6 +364,7 @@ class ShardedDMRG:
         """Small boundary SVD (dmrg.py:776, 793): rank 0 computes, everyone receives the same factors."""
         import torch.distributed as dist
         U, S, Vh = torch.linalg.svd(mat, full_matrices=False)
+        U, S, Vh = U.resolve_conj().contiguous(), S.contiguous(), Vh.resolve_conj().contiguous()
         src = dist.get_global_rank(self.group, 0)
         for t in (U, S, Vh):
             dist.broadcast(t, src=src, group=self.group)

@@ -67,7 +67,7 @@ def _gram_split(theta: torch.Tensor, maxdim: int, cutoff: float):
         Cm = theta @ top                                    # (m, keep) = U_k S_k
         Q, Rr = torch.linalg.qr(Cm)
         U = _fix_phase(Q, Rr)
-    return U, S, Vh, keep
+    return U.resolve_conj(), S, Vh.resolve_conj(), keep      # materialise lazy-conj views once
 
 
 def two_site_split(theta: torch.Tensor, maxdim: int, cutoff: float, *, fast_min: int = None
@@ -79,4 +79,4 @@ def two_site_split(theta: torch.Tensor, maxdim: int, cutoff: float, *, fast_min:
         return _gram_split(theta, maxdim, cutoff)
     U, S, Vh = torch.linalg.svd(theta, full_matrices=False)         # dmrg.py:685
     keep = _keep_from_spectrum(S, maxdim, cutoff)
-    return U[:, :keep], S, Vh[:keep, :], keep
+    return U[:, :keep].resolve_conj(), S, Vh[:keep, :].resolve_conj(), keep
