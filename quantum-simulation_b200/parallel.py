@@ -165,6 +165,11 @@ class CudaEngine:
         return lanczos_ground_state(v, op, args, **kw)
 
 
+def _real_view(t: torch.Tensor) -> torch.Tensor:
+    """NCCL reductions take real dtypes only; a complex tensor is reduced as its (re, im) float64 view."""
+    return torch.view_as_real(t) if t.is_complex() else t
+
+
 class _Env:
     """One cached environment: either replicated (full (W, chi, chi)) or this rank's row block (W, rows, chi)."""
     __slots__ = ("t", "sharded", "chi")
@@ -259,13 +264,13 @@ class ShardedDMRG:
             recv = torch.empty(rows * Wn * chi_new, dtype=partial.dtype, device=partial.device)
             if dist.get_backend(self.group) == "gloo":    # gloo (CPU tests) has no reduce-scatter: all-reduce + slice
                 flat = send.view(-1)
-                dist.all_reduce(flat, group=self.group)
+                dist.all_reduce(_real_view(flat), group=self.group)
                 recv.copy_(flat[self.rank * recv.numel(): (self.rank + 1) * recv.numel()])
-            else:
-                dist.reduce_scatter_tensor(recv, send.view(-1), group=self.group)
+            else:                                         # NCCL reduces real dtypes only: (re, im) pairs
+                dist.reduce_scatter_tensor(_real_view(recv), _real_view(send.view(-1)), group=self.group)
             self.comm["reduce_scatter_env"] += 1
             return _Env(recv.view(rows, Wn, chi_new).permute(1, 0, 2), True, chi_new)   # strided view, last dim contiguous
-        dist.all_reduce(partial, group=self.group)
+        dist.all_reduce(_real_view(partial), group=self.group)
         self.comm["all_reduce_env"] += 1
         return _Env(partial, False, chi_new)
 
