@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chi", type=int, default=2048)
     ap.add_argument("--dtype", default="f64", choices=["f64", "c128"])
+    ap.add_argument("--exchange", default="auto", choices=["auto", "fused", "nccl"],
+                    help="N>1: how theta shards are exchanged (auto = fused P2P push if available, else NCCL)")
     ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / lanczos / env / library legs")
     return ap.parse_args()
 
@@ -229,8 +231,24 @@ def run_ours(args):
     flops_total = flops_local * world
 
     theta_shard = theta.view(world, -1)[rank].clone() if world > 1 else None
+    exchange = "none"
+    fused = None
+    if world > 1:
+        exchange = "nccl all-gather of theta, then the matvec"
+        if args.exchange != "nccl":
+            try:           # all-gather fused into the matvec: P2P pushes + k-chunk gating of the step-1 GEMM
+                from quantum_simulation_b200.parallel import FusedShardedApplyMPO
+                fused = FusedShardedApplyMPO(chi, M1.shape[3] * M2.shape[3] * chi, dtype, dev)
+                exchange = "fused: P2P push of theta shards (qsb_push_shard) + arrival-gated step-1 GEMM, no NCCL on the data path"
+            except Exception as ex:
+                if args.exchange == "fused":
+                    raise
+                exchange += f" (fused path unavailable: {repr(ex)[:120]})"
 
     def step():
+        if fused is not None:
+            fused(theta_shard, L, M1, M2, R, out=out)
+            return
         if world > 1:      # the exchange step of the sharded matvec: block all-gather of theta
             dist.all_gather_into_tensor(theta, theta_shard)
         op(theta, L, M1, M2, R, out=out)
@@ -325,7 +343,8 @@ def run_ours(args):
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": args.dtype, "data": "synthetic", "config": workload_config(args, world), "clocks": clocks,
+            "dtype": args.dtype, "data": "synthetic", "config": dict(workload_config(args, world), exchange=exchange),
+            "clocks": clocks,
             "e2e": e2e, "gpu_launches": launches["total"], "launch_breakdown": launches, "roofline": roofline,
             "tflops": value / 1e3, "frac_of_fp64_tensor_peak": (value / 1e3 / world) / peak_tf if peak_tf else None}
 

@@ -77,6 +77,12 @@ typedef struct {
     const void* R;  int64_t R_stride[3];        /* (W_r, chi_r_out, chi_r_in), element strides */
     void*       out;                            /* (chi_l_out, d1_out, d2_out, chi_r_out) contiguous */
     void*       workspace; size_t workspace_bytes;
+    /* Fused all-gather -> matvec (multi-GPU, optional; n_chunks <= 1 disables it).  theta is the gathered vector
+       whose chi_l_in rows arrive in n_chunks equal blocks, block c pushed by rank c (qsb_push_shard).  Step 1 then
+       walks its k range block by block starting with block chunk_rot (the caller's own, already local) and reads
+       block c only once chunk_flags[c] >= chunk_epoch, so the transfer overlaps the first tiles. */
+    int n_chunks, chunk_rot, chunk_epoch;
+    const int* chunk_flags;
 } qsb_heff_desc;
 
 int qsb_heff_workspace_bytes(const qsb_heff_desc* d, size_t* bytes);
@@ -87,6 +93,13 @@ double qsb_heff_flops(const qsb_heff_desc* d);
    [0] before step 1, [1] after step 1 (GEMM), [2] after the MPO mix, [3] after step 4 (GEMM).
    count == 0 clears the hook.  Used by bench.py to time the dominant kernel inside the timed region. */
 int qsb_heff_set_stage_events(void* const* events, int count);
+
+/* Push one row shard of a vector into every rank's gathered buffer over NVLink and publish it:
+   dst[r] (r < world) is the address of THIS rank's block inside rank r's buffer (peer-mapped memory, 16-byte
+   aligned), flag[r] the address of THIS rank's arrival flag on rank r; after all stores, *flag[r] = epoch
+   (system-scope release).  `ticket` is a zero-initialised device int owned by the caller. */
+int qsb_push_shard(const void* src, size_t bytes, void* const* dst, int* const* flag, int world, int epoch,
+                   void* ticket, void* stream);
 
 /* ---- environment updates (dmrg.py:254-308) ----------------------------- */
 typedef struct {

@@ -31,7 +31,7 @@ EXPORTS = [
     "qsb_heff_workspace_bytes", "qsb_heff_apply", "qsb_heff_flops", "qsb_heff_set_stage_events",
     "qsb_env_workspace_bytes", "qsb_env_left", "qsb_env_right", "qsb_env_flops",
     "qsb_lz_scratch_bytes", "qsb_lz_dot", "qsb_lz_axpy_norm", "qsb_lz_scale", "qsb_lz_combine",
-    "qsb_strided_copy3", "qsb_gemm", "qsb_probe_dmma",
+    "qsb_strided_copy3", "qsb_gemm", "qsb_probe_dmma", "qsb_push_shard",
 ]
 
 
@@ -47,6 +47,8 @@ class HeffDesc(C.Structure):
         ("R", C.c_void_p), ("R_stride", C.c_int64 * 3),
         ("out", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("n_chunks", C.c_int), ("chunk_rot", C.c_int), ("chunk_epoch", C.c_int),
+        ("chunk_flags", C.c_void_p),
     ]
 
 
@@ -115,6 +117,7 @@ def load() -> C.CDLL:
     lib.qsb_lz_combine.argtypes = [i32, i64, i32, vp, i64, C.POINTER(C.c_double), vp, vp, i32, i32, vp, vp]
     lib.qsb_strided_copy3.argtypes = [i32, C.POINTER(i64), vp, C.POINTER(i64), vp, i32, vp]
     lib.qsb_gemm.argtypes = [C.POINTER(GemmDesc), vp]
+    lib.qsb_push_shard.argtypes = [vp, C.c_size_t, C.POINTER(vp), C.POINTER(vp), i32, i32, vp, vp]
     lib.qsb_probe_dmma.argtypes = [i32, C.POINTER(C.c_double), vp, vp]
     for name in EXPORTS:          # every symbol include/qsb200.h declares must be exported
         getattr(lib, name)
@@ -230,10 +233,13 @@ def heff_flops(psi, L, M1, M2, R) -> float:
     return float(load().qsb_heff_flops(C.byref(heff_desc(psi, L, M1, M2, R, None))))
 
 
-def _impl_heff_apply(psi, L, M1, M2, R, out) -> None:
+def _impl_heff_apply(psi, L, M1, M2, R, out, gate=None) -> None:
     lib = load()
     dev = _require_cuda(psi, L, M1, M2, R, out)
     d = heff_desc(psi, L, M1, M2, R, out)
+    if gate is not None:                   # (flags tensor, n_chunks, rot, epoch): fused all-gather -> matvec
+        flags, d.n_chunks, d.chunk_rot, d.chunk_epoch = gate
+        d.chunk_flags = flags.data_ptr()
     nb = C.c_size_t(0)
     check(lib.qsb_heff_workspace_bytes(C.byref(d), C.byref(nb)), "ApplyMPO")
     ws = workspace(dev, nb.value)
@@ -241,6 +247,20 @@ def _impl_heff_apply(psi, L, M1, M2, R, out) -> None:
     d.workspace_bytes = ws.numel()
     with torch.cuda.device(dev):
         check(lib.qsb_heff_apply(C.byref(d), _stream()), "ApplyMPO")
+
+
+def _impl_heff_apply_gated(psi, L, M1, M2, R, out, flags, n_chunks: int, rot: int, epoch: int) -> None:
+    _impl_heff_apply(psi, L, M1, M2, R, out, gate=(flags, n_chunks, rot, epoch))
+
+
+def _impl_push_shard(src, dst_ptrs: Sequence[int], flag_ptrs: Sequence[int], epoch: int, ticket) -> None:
+    dev = _require_cuda(src, ticket)
+    world = len(dst_ptrs)
+    dp = (C.c_void_p * world)(*[C.c_void_p(int(p)) for p in dst_ptrs])
+    fp = (C.c_void_p * world)(*[C.c_void_p(int(p)) for p in flag_ptrs])
+    with torch.cuda.device(dev):
+        check(load().qsb_push_shard(src.data_ptr(), src.numel() * src.element_size(), dp, fp, world, epoch,
+                                    ticket.data_ptr(), _stream()), "push_shard")
 
 
 def env_desc(env: torch.Tensor, M: torch.Tensor, site: torch.Tensor, out: Optional[torch.Tensor],
@@ -421,6 +441,9 @@ def register_ops() -> None:
         return
     tl = torch.library.Library("qsb200", "DEF")
     tl.define("heff_apply(Tensor psi, Tensor L, Tensor M1, Tensor M2, Tensor R, Tensor(a!) out) -> ()")
+    tl.define("heff_apply_gated(Tensor psi, Tensor L, Tensor M1, Tensor M2, Tensor R, Tensor(a!) out, Tensor flags, "
+              "int n_chunks, int rot, int epoch) -> ()")
+    tl.define("push_shard(Tensor src, int[] dst_ptrs, int[] flag_ptrs, int epoch, Tensor(a!) ticket) -> ()")
     tl.define("env_left(Tensor env, Tensor M, Tensor site, Tensor(a!) out) -> ()")
     tl.define("env_right(Tensor env, Tensor M, Tensor site, Tensor(a!) out) -> ()")
     tl.define("env_left_rows(Tensor env, Tensor M, Tensor site, Tensor site_bra, Tensor(a!) out) -> ()")
@@ -433,6 +456,8 @@ def register_ops() -> None:
     tl.define("lz_combine(Tensor X, int m, int ldx, float[] y, Tensor(a!) dst, int n, Tensor(b!) scal, "
               "int norm_idx, int flags, Tensor(c!) scratch) -> ()")
     tl.impl("heff_apply", _impl_heff_apply, "CUDA")
+    tl.impl("heff_apply_gated", _impl_heff_apply_gated, "CUDA")
+    tl.impl("push_shard", _impl_push_shard, "CUDA")
     tl.impl("env_left", _impl_env_left, "CUDA")
     tl.impl("env_right", _impl_env_right, "CUDA")
     tl.impl("env_left_rows", _impl_env_left_rows, "CUDA")

@@ -33,6 +33,9 @@ struct GemmArgs {
     const void* B; long long b_rs, b_ks, b_ps, b_zs; int conjB;   // b_rs: stride of n
     void*       C; long long c_ms, c_ns, c_zs;
     int force_path;                 // 0 auto, 1 TMA, 2 cp.async
+    // optional k-chunk gating (TMA path only): see TArgs in gemm_tma.cu
+    int ksplit = 1, krot = 0, kepoch = 0;
+    const int* kflags = nullptr;
 };
 int gemm_launch(const GemmArgs& g, cudaStream_t stream);
 

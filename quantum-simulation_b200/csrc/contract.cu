@@ -381,6 +381,11 @@ extern "C" int qsb_heff_apply(const qsb_heff_desc* d, void* stream_) {
     g1.B = d->theta; g1.b_rs = 1; g1.b_ks = N1; g1.b_ps = 0; g1.b_zs = 0; g1.conjB = 0;
     g1.C = T1; g1.c_ms = N1; g1.c_ns = 1; g1.c_zs = clo * N1;
     g1.force_path = 0;
+    if (d->n_chunks > 1) {           // fused all-gather -> GEMM: gate the k chunks on their arrival flags
+        if (!d->chunk_flags) return QSB_ERR_ARG;
+        g1.ksplit = d->n_chunks; g1.krot = d->chunk_rot; g1.kepoch = d->chunk_epoch; g1.kflags = d->chunk_flags;
+        g1.force_path = 1;
+    }
     if ((rc = gemm_launch(g1, stream))) return rc;
     stage_mark(1, stream);
 
@@ -405,6 +410,59 @@ extern "C" int qsb_heff_apply(const qsb_heff_desc* d, void* stream_) {
     rc = gemm_launch(g4, stream);
     stage_mark(3, stream);
     return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// push a row shard to every peer's gathered buffer (P2P stores over NVLink) and publish it
+// ---------------------------------------------------------------------------------------------
+namespace qsb {
+constexpr int kMaxPeers = 16;
+struct PushArgs {
+    const uint4* src; long long n16;
+    uint4* dst[kMaxPeers]; int* flag[kMaxPeers];
+    int world, epoch;
+    unsigned int* ticket;
+};
+__global__ void __launch_bounds__(256) push_shard_kernel(const PushArgs a) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < a.n16; u += stride) {
+        const uint4 v = __ldg(a.src + u);
+#pragma unroll 1
+        for (int r = 0; r < a.world; ++r) a.dst[r][u] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ bool last;
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(a.ticket, 1u);
+        last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last && threadIdx.x < a.world) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.s32 [%0], %1;" :: "l"(a.flag[threadIdx.x]), "r"(a.epoch) : "memory");
+        if (threadIdx.x == 0) *a.ticket = 0;
+    }
+}
+}  // namespace qsb
+
+extern "C" int qsb_push_shard(const void* src, size_t bytes, void* const* dst, int* const* flag, int world, int epoch,
+                              void* ticket, void* stream) {
+    if (!src || !dst || !flag || !ticket || world < 1 || world > kMaxPeers) return QSB_ERR_ARG;
+    if (bytes % 16 != 0 || !aligned16(src)) return QSB_ERR_STRIDE;
+    PushArgs a{};
+    a.src = (const uint4*)src; a.n16 = (long long)(bytes / 16);
+    for (int r = 0; r < world; ++r) {
+        if (!dst[r] || !flag[r] || !aligned16(dst[r])) return QSB_ERR_ARG;
+        a.dst[r] = (uint4*)dst[r]; a.flag[r] = flag[r];
+    }
+    a.world = world; a.epoch = epoch; a.ticket = (unsigned int*)ticket;
+    long long blocks = (a.n16 + 255) / 256;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    if (blocks < 1) blocks = 1;
+    push_shard_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+    ++g_count_other;
+    return check_launch();
 }
 
 extern "C" int qsb_heff_set_stage_events(void* const* events, int count) {

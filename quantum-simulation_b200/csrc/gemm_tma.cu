@@ -40,6 +40,10 @@ struct TArgs {
     int a_has_p, a_has_z, b_has_p, b_has_z;     // 0 when that stride is 0 (coordinate pinned to 0)
     char* C; long long c_ms, c_ns, c_zs;
     double sgnA, sgnB;
+    // k-chunk gating (fused all-gather -> GEMM): the k range is ksplit equal chunks, chunk c becomes readable when
+    // kflags[c] >= kepoch (set by the peer that pushed it); chunks are visited starting from chunk krot
+    int ksplit, krot, kepoch;
+    const int* kflags;
 };
 
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
@@ -203,6 +207,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     Sched ps; ps.init(sk.U_sk, sk.ipt, sk.T_sk, sk.dp_waves, G, cta);
     int p_tile = -1, p_it = 0, p_it1 = 0, p_m0 = 0, p_n0 = 0, p_z = 0;
     int pj = 0;                              // CTA-local index of the next k-iteration to issue
+    int p_chunk_ok = -1;                     // last gated k chunk known to have arrived
     bool p_more = true;
     auto produce = [&]() {                   // issue one k-iteration (if any is left); thread 0 only
         if (p_it == p_it1) {
@@ -213,7 +218,24 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         }
         const int slot = pj % S;
         if (pj >= S) mbar_wait_spin(bar_empty + 8 * slot, ((pj / S) + 1) & 1);
-        const int p = p_it / ktiles, k0 = (p_it - p * ktiles) * C::BK;
+        int p = p_it / ktiles, k0 = (p_it - p * ktiles) * C::BK;
+        if (g.ksplit > 1) {                  // P == 1 here: visit the k chunks in rotated order, gated on arrival
+            const int per = ktiles / g.ksplit;
+            const int c = p_it / per;
+            int kc = c + g.krot; if (kc >= g.ksplit) kc -= g.ksplit;
+            if (kc != p_chunk_ok) {
+                int v;
+                const long long t0 = clock64();
+                do {
+                    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(g.kflags + kc) : "memory");
+                    if (v < g.kepoch && clock64() - t0 > 20000000000LL) __trap();
+                } while (v < g.kepoch);
+                asm volatile("fence.proxy.async.global;" ::: "memory");   // peer-written data -> TMA (async proxy) reads
+                p_chunk_ok = kc;
+            }
+            p = 0;
+            k0 = (kc * per + (p_it - c * per)) * C::BK;
+        }
         const uint32_t sa = sbase + slot * STAGE, sb = sa + A_BYTES, bar = bar_full + 8 * slot;
         mbar_expect_tx(bar, STAGE);
         if constexpr (A_KC) tma_load_4d(sa, &mapA, bar, k0 * KMUL, p_m0, g.a_has_p ? p : 0, g.a_has_z ? p_z : 0);
@@ -545,6 +567,12 @@ int gemm_tma_try(const GemmArgs& g, cudaStream_t stream, bool* used) {
     t.b_has_p = (b.has_p && g.P > 1); t.b_has_z = (b.has_z && g.Z > 1);
     t.C = (char*)g.C; t.c_ms = g.c_ms; t.c_ns = g.c_ns; t.c_zs = g.Z > 1 ? g.c_zs : 0;
     t.sgnA = g.conjA ? -1.0 : 1.0; t.sgnB = g.conjB ? -1.0 : 1.0;
+    t.ksplit = 1; t.krot = 0; t.kepoch = 0; t.kflags = nullptr;
+    if (g.ksplit > 1) {
+        const int ktiles = (g.K + BK - 1) / BK;
+        if (g.P != 1 || g.K % BK != 0 || ktiles % g.ksplit != 0 || !g.kflags) return QSB_ERR_STRIDE;
+        t.ksplit = g.ksplit; t.krot = g.krot % g.ksplit; t.kepoch = g.kepoch; t.kflags = g.kflags;
+    }
     int rc;
     if (cplx) {
         if (a_kc) rc = b_kc ? launch_tma<true, true, true>(ma, mb, t, g.Z, stream) : launch_tma<true, true, false>(ma, mb, t, g.Z, stream);

@@ -19,7 +19,7 @@ import torch
 from .eigensolver import _lanczos_impl, _CUDA_OPS
 
 __all__ = ["row_partition", "ShardedApplyMPO", "lanczos_ground_state_sharded", "shard_rows", "gather_rows",
-           "ShardedDMRG", "CudaEngine"]
+           "ShardedDMRG", "CudaEngine", "FusedShardedApplyMPO"]
 
 
 def row_partition(chi: int, world: int) -> List[Tuple[int, int]]:
@@ -103,6 +103,68 @@ class ShardedApplyMPO:
     def __call__(self, v_shard, L_rows, M1, M2, R, out=None):
         full = self.gather(v_shard)                      # the one exchange step of the sharded matvec
         return self.local_op(full, L_rows, M1, M2, R, out=out)
+
+
+class FusedShardedApplyMPO:
+    """Sharded H_eff . theta with the all-gather FUSED into the matvec (no NCCL call on the data path).
+
+    Every rank pushes its row shard of the input vector straight into all peers' gathered buffers with P2P stores
+    over NVLink (``qsb_push_shard``: one kernel, then a system-scope release of a per-source arrival flag).  The
+    step-1 GEMM then walks its k range source-rank block by source-rank block, starting with the rank's own block
+    (already local) and touching block c only once its flag shows it has landed -- the transfer overlaps the first
+    tiles instead of preceding the kernel (``qsb_heff_desc.n_chunks / chunk_flags``).  The gathered buffers and flags
+    live in ``torch.distributed._symmetric_memory`` (peer-mapped allocations); buffers are double-buffered by epoch
+    parity, flags are monotonic epochs, so a rank that runs one step ahead never overwrites data a peer still reads.
+    """
+
+    def __init__(self, chi_l: int, per_row: int, dtype: torch.dtype, device, group: Any = None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        self._ops = _lib.ops
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        es = torch.empty(0, dtype=dtype).element_size()
+        bk = 8 if dtype.is_complex else 16
+        if chi_l % self.world != 0 or (chi_l // bk) % self.world != 0 or chi_l % bk != 0:
+            raise ValueError(f"fused sharded matvec needs chi_l divisible by {bk} * world_size (got chi_l={chi_l}, "
+                             f"world={self.world}); use ShardedApplyMPO")
+        self.chi_l, self.per_row = chi_l, per_row
+        self.lo, self.hi = row_partition(chi_l, self.world)[self.rank]
+        n = chi_l * per_row
+        shard_bytes = (n // self.world) * es
+        stride = (n * es + 255) // 256 * 256
+        total = 256 + 2 * stride
+        try:
+            symm_mem.enable_symm_mem_for_group(self.group.group_name)
+        except Exception:
+            pass
+        self._store = symm_mem.empty(total, dtype=torch.uint8, device=device)
+        self._store.zero_()
+        torch.cuda.synchronize(device)
+        self._hdl = symm_mem.rendezvous(self._store, self.group.group_name)
+        ptrs = [int(p) for p in self._hdl.buffer_ptrs]
+        self.flags = self._store[:256].view(torch.int32)
+        self.bufs = [self._store[256 + b * stride: 256 + b * stride + n * es].view(dtype) for b in (0, 1)]
+        self.dst_ptrs = [[ptrs[r] + 256 + b * stride + self.rank * shard_bytes for r in range(self.world)]
+                         for b in (0, 1)]
+        self.flag_ptrs = [ptrs[r] + 4 * self.rank for r in range(self.world)]
+        self.ticket = torch.zeros(1, dtype=torch.int32, device=device)
+        self.epoch = 0
+        dist.barrier(group=self.group)
+
+    def __call__(self, v_shard, L_rows, M1, M2, R, out=None):
+        self.epoch += 1
+        b = self.epoch & 1
+        v = v_shard.reshape(-1)
+        if not v.is_contiguous():
+            v = v.contiguous()
+        if out is None:
+            out = torch.empty(L_rows.shape[1] * M1.shape[2] * M2.shape[2] * R.shape[1], dtype=v.dtype, device=v.device)
+        self._ops.push_shard(v, self.dst_ptrs[b], self.flag_ptrs, self.epoch, self.ticket)
+        self._ops.heff_apply_gated(self.bufs[b], L_rows, M1, M2, R, out, self.flags, self.world, self.rank, self.epoch)
+        return out
 
 
 def lanczos_ground_state_sharded(initial_shard: torch.Tensor, linear_operator: Callable,
