@@ -31,7 +31,7 @@ EXPORTS = [
     "qsb_heff_workspace_bytes", "qsb_heff_apply", "qsb_heff_flops", "qsb_heff_set_stage_events",
     "qsb_env_workspace_bytes", "qsb_env_left", "qsb_env_right", "qsb_env_flops",
     "qsb_lz_scratch_bytes", "qsb_lz_dot", "qsb_lz_axpy_norm", "qsb_lz_scale", "qsb_lz_combine",
-    "qsb_strided_copy3", "qsb_gemm", "qsb_probe_dmma", "qsb_push_shard",
+    "qsb_strided_copy3", "qsb_gemm", "qsb_probe_dmma", "qsb_push_shard", "qsb_push_shard_dma",
 ]
 
 
@@ -118,6 +118,7 @@ def load() -> C.CDLL:
     lib.qsb_strided_copy3.argtypes = [i32, C.POINTER(i64), vp, C.POINTER(i64), vp, i32, vp]
     lib.qsb_gemm.argtypes = [C.POINTER(GemmDesc), vp]
     lib.qsb_push_shard.argtypes = [vp, C.c_size_t, C.POINTER(vp), C.POINTER(vp), i32, i32, vp, vp]
+    lib.qsb_push_shard_dma.argtypes = [vp, C.c_size_t, C.POINTER(vp), C.POINTER(vp), i32, i32, i32, vp]
     lib.qsb_probe_dmma.argtypes = [i32, C.POINTER(C.c_double), vp, vp]
     for name in EXPORTS:          # every symbol include/qsb200.h declares must be exported
         getattr(lib, name)
@@ -261,6 +262,18 @@ def _impl_push_shard(src, dst_ptrs: Sequence[int], flag_ptrs: Sequence[int], epo
     with torch.cuda.device(dev):
         check(load().qsb_push_shard(src.data_ptr(), src.numel() * src.element_size(), dp, fp, world, epoch,
                                     ticket.data_ptr(), _stream()), "push_shard")
+
+
+def push_shard_dma(src: torch.Tensor, dst_ptrs: Sequence[int], flag_ptrs: Sequence[int], my_rank: int,
+                   epoch: int) -> None:
+    """Copy-engine push on the CURRENT stream (callers put it on a side stream)."""
+    dev = _require_cuda(src)
+    world = len(dst_ptrs)
+    dp = (C.c_void_p * world)(*[C.c_void_p(int(p)) for p in dst_ptrs])
+    fp = (C.c_void_p * world)(*[C.c_void_p(int(p)) for p in flag_ptrs])
+    with torch.cuda.device(dev):
+        check(load().qsb_push_shard_dma(src.data_ptr(), src.numel() * src.element_size(), dp, fp, world, my_rank,
+                                        epoch, _stream()), "push_shard_dma")
 
 
 def env_desc(env: torch.Tensor, M: torch.Tensor, site: torch.Tensor, out: Optional[torch.Tensor],

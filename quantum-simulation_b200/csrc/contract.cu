@@ -465,6 +465,41 @@ extern "C" int qsb_push_shard(const void* src, size_t bytes, void* const* dst, i
     return check_launch();
 }
 
+// copy-engine variant: (world) peer memcpys + stream-ordered 32-bit flag writes, no SM involved, so it runs
+// concurrently with the persistent GEMM (which occupies every SM) when enqueued on a side stream
+typedef CUresult (*WriteValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+static WriteValue32Fn get_write_value32() {
+    static WriteValue32Fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (WriteValue32Fn)p;
+        (void)cudaGetLastError();
+    }
+    return fn;
+}
+
+extern "C" int qsb_push_shard_dma(const void* src, size_t bytes, void* const* dst, int* const* flag, int world,
+                                  int my_rank, int epoch, void* stream_) {
+    if (!src || !dst || !flag || world < 1 || world > qsb::kMaxPeers || my_rank < 0 || my_rank >= world)
+        return QSB_ERR_ARG;
+    WriteValue32Fn wv = get_write_value32();
+    if (!wv) return QSB_ERR_DEVICE;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    for (int i = 0; i < world; ++i) {
+        const int r = (my_rank + i) % world;          // own block first, then the peers in ring order
+        if (!dst[r] || !flag[r]) return QSB_ERR_ARG;
+        int rc = check_cuda(cudaMemcpyAsync(dst[r], src, bytes, cudaMemcpyDeviceToDevice, stream));
+        if (rc) return rc;
+        if (wv((CUstream)stream, (CUdeviceptr)flag[r], (cuuint32_t)epoch, 0) != CUDA_SUCCESS) return QSB_ERR_LAUNCH;
+    }
+    return QSB_OK;
+}
+
 extern "C" int qsb_heff_set_stage_events(void* const* events, int count) {
     if (count != 0 && (count != 4 || !events)) return QSB_ERR_ARG;
     for (int i = 0; i < count; ++i) g_stage_events[i] = (cudaEvent_t)events[i];

@@ -117,11 +117,16 @@ class FusedShardedApplyMPO:
     parity, flags are monotonic epochs, so a rank that runs one step ahead never overwrites data a peer still reads.
     """
 
-    def __init__(self, chi_l: int, per_row: int, dtype: torch.dtype, device, group: Any = None):
+    def __init__(self, chi_l: int, per_row: int, dtype: torch.dtype, device, group: Any = None, push: str = "dma"):
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
         from . import _lib
         self._ops = _lib.ops
+        self._lib = _lib
+        if push not in ("dma", "sm"):
+            raise ValueError("push must be 'dma' (copy engines on a side stream) or 'sm' (one store kernel)")
+        self.push = push
+        self._side = torch.cuda.Stream(device=device) if push == "dma" else None
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
         self.rank = dist.get_rank(self.group)
@@ -162,8 +167,22 @@ class FusedShardedApplyMPO:
             v = v.contiguous()
         if out is None:
             out = torch.empty(L_rows.shape[1] * M1.shape[2] * M2.shape[2] * R.shape[1], dtype=v.dtype, device=v.device)
-        self._ops.push_shard(v, self.dst_ptrs[b], self.flag_ptrs, self.epoch, self.ticket)
+        if self.push == "sm":
+            self._ops.push_shard(v, self.dst_ptrs[b], self.flag_ptrs, self.epoch, self.ticket)
+            self._ops.heff_apply_gated(self.bufs[b], L_rows, M1, M2, R, out, self.flags, self.world, self.rank,
+                                       self.epoch)
+            return out
+        # copy engines on a side stream: the pushes run WHILE the gated GEMM already works on the local block
+        main = torch.cuda.current_stream(v.device)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        self._side.wait_event(ready)
+        with torch.cuda.stream(self._side):
+            self._lib.push_shard_dma(v, self.dst_ptrs[b], self.flag_ptrs, self.rank, self.epoch)
+            done = torch.cuda.Event()
+            done.record(self._side)
         self._ops.heff_apply_gated(self.bufs[b], L_rows, M1, M2, R, out, self.flags, self.world, self.rank, self.epoch)
+        main.wait_event(done)            # v_shard may be reused once our outgoing copies have left
         return out
 
 

@@ -63,7 +63,7 @@ def main():
     torch.cuda.synchronize()
     t_1 = time.perf_counter() - t0
     # fused all-gather -> matvec (P2P push + gated GEMM) against the same single-GPU rows, then timed vs NCCL
-    fused_err, t_fused, t_nccl, fused_note = -1.0, 0.0, 0.0, "ok"
+    fused_err, t_fused, t_nccl, fused_note, t_fused_sm = -1.0, 0.0, 0.0, "ok", 0.0
     try:
         fop = parallel.FusedShardedApplyMPO(chi, per_row, dtype, dev)
         o2 = torch.empty_like(out)
@@ -88,6 +88,10 @@ def main():
             e1.record(); e1.synchronize()
             return e0.elapsed_time(e1) / n
         t_fused = timeit(lambda: fop(shard, L_rows, M1, M2, R, out=o2))
+        fop_sm = parallel.FusedShardedApplyMPO(chi, per_row, dtype, dev, push="sm")
+        fop_sm(shard, L_rows, M1, M2, R, out=o2)
+        fused_err = max(fused_err, float(torch.linalg.norm(o2 - ref[lo * per_row: hi * per_row]) / torch.linalg.norm(ref)))
+        t_fused_sm = timeit(lambda: fop_sm(shard, L_rows, M1, M2, R, out=o2))
         t_nccl = timeit(lambda: sop(shard, L_rows, M1, M2, R, out=o2))
     except Exception as ex:
         fused_note = repr(ex)[:300]
@@ -126,7 +130,7 @@ def main():
                           "lanczos_solve_s_single_gpu": t_1, "dmrg_L20_chi": chi_d,
                           "dmrg_max_rel_dev_per_update": float(errs[3]), "dmrg_bond_dims_equal": bool(errs[4] == 0.0),
                           "dmrg_s_single": t_single, "dmrg_s_sharded": t_shard, "dmrg_comm": d2.comm, "fused_matvec_rel_err": float(ferr),
-                          "fused_ms": t_fused, "nccl_ms": t_nccl, "fused_note": fused_note, "ok": ok}))
+                          "fused_dma_ms": t_fused, "fused_sm_ms": t_fused_sm, "nccl_ms": t_nccl, "fused_note": fused_note, "ok": ok}))
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
 
