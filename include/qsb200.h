@@ -100,11 +100,11 @@ int qsb_heff_set_stage_events(void* const* events, int count);
    (system-scope release).  `ticket` is a zero-initialised device int owned by the caller. */
 int qsb_push_shard(const void* src, size_t bytes, void* const* dst, int* const* flag, int world, int epoch,
                    void* ticket, void* stream);
-/* Same contract on the copy engines: one peer cudaMemcpyAsync + one stream-ordered 32-bit flag write
-   (cuStreamWriteValue32) per rank, own block first.  No SM is used, so on a side stream it overlaps the
-   persistent GEMM of the matvec that consumes the blocks. */
-int qsb_push_shard_dma(const void* src, size_t bytes, void* const* dst, int* const* flag, int world, int my_rank,
-                       int epoch, void* stream);
+/* Same contract on the copy engines: for each of the `count` destinations, in the given order, one peer
+   cudaMemcpyAsync followed by one stream-ordered 32-bit flag write (cuStreamWriteValue32).  No SM is used, so on a
+   side stream it overlaps the persistent GEMM of the matvec that consumes the blocks. */
+int qsb_push_shard_dma(const void* src, size_t bytes, void* const* dst, int* const* flag, int count, int epoch,
+                       void* stream);
 
 /* ---- environment updates (dmrg.py:254-308) ----------------------------- */
 typedef struct {

@@ -118,7 +118,7 @@ def load() -> C.CDLL:
     lib.qsb_strided_copy3.argtypes = [i32, C.POINTER(i64), vp, C.POINTER(i64), vp, i32, vp]
     lib.qsb_gemm.argtypes = [C.POINTER(GemmDesc), vp]
     lib.qsb_push_shard.argtypes = [vp, C.c_size_t, C.POINTER(vp), C.POINTER(vp), i32, i32, vp, vp]
-    lib.qsb_push_shard_dma.argtypes = [vp, C.c_size_t, C.POINTER(vp), C.POINTER(vp), i32, i32, i32, vp]
+    lib.qsb_push_shard_dma.argtypes = [vp, C.c_size_t, C.POINTER(vp), C.POINTER(vp), i32, i32, vp]
     lib.qsb_probe_dmma.argtypes = [i32, C.POINTER(C.c_double), vp, vp]
     for name in EXPORTS:          # every symbol include/qsb200.h declares must be exported
         getattr(lib, name)
@@ -264,16 +264,15 @@ def _impl_push_shard(src, dst_ptrs: Sequence[int], flag_ptrs: Sequence[int], epo
                                     ticket.data_ptr(), _stream()), "push_shard")
 
 
-def push_shard_dma(src: torch.Tensor, dst_ptrs: Sequence[int], flag_ptrs: Sequence[int], my_rank: int,
-                   epoch: int) -> None:
-    """Copy-engine push on the CURRENT stream (callers put it on a side stream)."""
+def push_shard_dma(src: torch.Tensor, dst_ptrs: Sequence[int], flag_ptrs: Sequence[int], epoch: int) -> None:
+    """Copy-engine push, destinations in the given order, on the CURRENT stream (callers use side streams)."""
     dev = _require_cuda(src)
     world = len(dst_ptrs)
     dp = (C.c_void_p * world)(*[C.c_void_p(int(p)) for p in dst_ptrs])
     fp = (C.c_void_p * world)(*[C.c_void_p(int(p)) for p in flag_ptrs])
     with torch.cuda.device(dev):
-        check(load().qsb_push_shard_dma(src.data_ptr(), src.numel() * src.element_size(), dp, fp, world, my_rank,
-                                        epoch, _stream()), "push_shard_dma")
+        check(load().qsb_push_shard_dma(src.data_ptr(), src.numel() * src.element_size(), dp, fp, world, epoch,
+                                        _stream()), "push_shard_dma")
 
 
 def env_desc(env: torch.Tensor, M: torch.Tensor, site: torch.Tensor, out: Optional[torch.Tensor],

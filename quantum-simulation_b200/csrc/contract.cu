@@ -483,19 +483,17 @@ static WriteValue32Fn get_write_value32() {
     return fn;
 }
 
-extern "C" int qsb_push_shard_dma(const void* src, size_t bytes, void* const* dst, int* const* flag, int world,
-                                  int my_rank, int epoch, void* stream_) {
-    if (!src || !dst || !flag || world < 1 || world > qsb::kMaxPeers || my_rank < 0 || my_rank >= world)
-        return QSB_ERR_ARG;
+extern "C" int qsb_push_shard_dma(const void* src, size_t bytes, void* const* dst, int* const* flag, int count,
+                                  int epoch, void* stream_) {
+    if (!src || !dst || !flag || count < 0 || count > qsb::kMaxPeers) return QSB_ERR_ARG;
     WriteValue32Fn wv = get_write_value32();
     if (!wv) return QSB_ERR_DEVICE;
     cudaStream_t stream = (cudaStream_t)stream_;
-    for (int i = 0; i < world; ++i) {
-        const int r = (my_rank + i) % world;          // own block first, then the peers in ring order
-        if (!dst[r] || !flag[r]) return QSB_ERR_ARG;
-        int rc = check_cuda(cudaMemcpyAsync(dst[r], src, bytes, cudaMemcpyDeviceToDevice, stream));
+    for (int i = 0; i < count; ++i) {                 // in the caller's order
+        if (!dst[i] || !flag[i]) return QSB_ERR_ARG;
+        int rc = check_cuda(cudaMemcpyAsync(dst[i], src, bytes, cudaMemcpyDeviceToDevice, stream));
         if (rc) return rc;
-        if (wv((CUstream)stream, (CUdeviceptr)flag[r], (cuuint32_t)epoch, 0) != CUDA_SUCCESS) return QSB_ERR_LAUNCH;
+        if (wv((CUstream)stream, (CUdeviceptr)flag[i], (cuuint32_t)epoch, 0) != CUDA_SUCCESS) return QSB_ERR_LAUNCH;
     }
     return QSB_OK;
 }

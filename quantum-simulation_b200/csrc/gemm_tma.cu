@@ -127,10 +127,10 @@ template <bool CPLX, bool KC> struct FragAddr {
 // The tile count is rarely a multiple of the SM count (chi = 2048, 8 GPUs: 128 tiles on 148 SMs), so the last
 // partial wave would idle SMs.  The grid is one persistent CTA per SM.  Tiles [0, T_sk) -- the remainder wave plus
 // one full wave -- are split in k ("stream-K"): their T_sk * ipt k-iterations are divided evenly over the CTAs;
-// the remaining tiles are dealt round-robin, one whole tile per CTA per wave.  A CTA walks its stream-K range from
-// the END backwards, so the piece it shares with the next-lower CTA comes last: the CTA that owns the final
-// k-iteration of a tile ("finisher") adds the partial accumulators its lower-indexed neighbours wrote at the very
-// START of their own walk.  A CTA therefore only ever waits for lower-indexed CTAs (no co-residency assumption),
+// the remaining tiles are dealt round-robin, one whole tile per CTA per wave, and are done FIRST.  A CTA then walks
+// its stream-K range from the END backwards, so the piece it shares with the next-lower CTA comes last: the CTA that
+// owns the final k-iteration of a tile ("finisher") adds the partial accumulators its lower-indexed neighbours wrote
+// at the START of their own walk.  A CTA therefore only ever waits for lower-indexed CTAs (no co-residency assumption),
 // and the partial sums are added in CTA order (deterministic).
 struct Sched {
     long long u0, seg_end;      // stream-K unit range [u0, seg_end) still to do (units = k-iterations)
@@ -142,16 +142,16 @@ struct Sched {
     }
     // next segment: k-iterations [it0, it1) of tile `tile`
     __device__ __forceinline__ bool next(int& tile, int& it0, int& it1) {
-        if (seg_end > u0) {
+        if (dp_next < dp_waves) {           // whole tiles first (they start at k = 0: the gated matvec wants that)
+            tile = T_sk + dp_next * G + c; it0 = 0; it1 = ipt; ++dp_next;
+            return true;
+        }
+        if (seg_end > u0) {                 // then this CTA's stream-K range, from its end backwards
             tile = (int)((seg_end - 1) / ipt);
             const long long tb = (long long)tile * ipt;
             const long long b = u0 > tb ? u0 : tb;
             it0 = (int)(b - tb); it1 = (int)(seg_end - tb);
             seg_end = b;
-            return true;
-        }
-        if (dp_next < dp_waves) {
-            tile = T_sk + dp_next * G + c; it0 = 0; it1 = ipt; ++dp_next;
             return true;
         }
         return false;

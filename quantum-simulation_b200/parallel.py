@@ -126,7 +126,7 @@ class FusedShardedApplyMPO:
         if push not in ("dma", "sm"):
             raise ValueError("push must be 'dma' (copy engines on a side stream) or 'sm' (one store kernel)")
         self.push = push
-        self._side = torch.cuda.Stream(device=device) if push == "dma" else None
+        self._side = [torch.cuda.Stream(device=device) for _ in range(2)] if push == "dma" else []
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
         self.rank = dist.get_rank(self.group)
@@ -157,6 +157,9 @@ class FusedShardedApplyMPO:
         self.flag_ptrs = [ptrs[r] + 4 * self.rank for r in range(self.world)]
         self.ticket = torch.zeros(1, dtype=torch.int32, device=device)
         self.epoch = 0
+        # push order: own block, then rank-1, rank-2, ...  Rank m therefore RECEIVES blocks m+1, m+2, ... in that
+        # order -- the order in which its gated GEMM walks the k chunks (rotation starts at its own block).
+        self._order = [(self.rank - i) % self.world for i in range(self.world)]
         dist.barrier(group=self.group)
 
     def __call__(self, v_shard, L_rows, M1, M2, R, out=None):
@@ -176,13 +179,21 @@ class FusedShardedApplyMPO:
         main = torch.cuda.current_stream(v.device)
         ready = torch.cuda.Event()
         ready.record(main)
-        self._side.wait_event(ready)
-        with torch.cuda.stream(self._side):
-            self._lib.push_shard_dma(v, self.dst_ptrs[b], self.flag_ptrs, self.rank, self.epoch)
-            done = torch.cuda.Event()
-            done.record(self._side)
+        dones = []
+        for si, side in enumerate(self._side):       # two copy streams: destinations dealt alternately
+            targets = self._order[si::len(self._side)]
+            if not targets:
+                continue
+            side.wait_event(ready)
+            with torch.cuda.stream(side):
+                self._lib.push_shard_dma(v, [self.dst_ptrs[b][r] for r in targets],
+                                         [self.flag_ptrs[r] for r in targets], self.epoch)
+                done = torch.cuda.Event()
+                done.record(side)
+                dones.append(done)
         self._ops.heff_apply_gated(self.bufs[b], L_rows, M1, M2, R, out, self.flags, self.world, self.rank, self.epoch)
-        main.wait_event(done)            # v_shard may be reused once our outgoing copies have left
+        for done in dones:
+            main.wait_event(done)        # v_shard may be reused once our outgoing copies have left
         return out
 
 
