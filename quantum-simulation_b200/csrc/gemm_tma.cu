@@ -127,7 +127,7 @@ template <bool CPLX, bool KC> struct FragAddr {
 // The tile count is rarely a multiple of the SM count (chi = 2048, 8 GPUs: 128 tiles on 148 SMs), so the last
 // partial wave would idle SMs.  The grid is one persistent CTA per SM.  Tiles [0, T_sk) -- the remainder wave plus
 // one full wave -- are split in k ("stream-K"): their T_sk * ipt k-iterations are divided evenly over the CTAs;
-// the remaining tiles are dealt round-robin, one whole tile per CTA per wave, and are done FIRST.  A CTA then walks
+// the remaining tiles are dealt round-robin, one whole tile per CTA per wave.  A CTA walks
 // its stream-K range from the END backwards, so the piece it shares with the next-lower CTA comes last: the CTA that
 // owns the final k-iteration of a tile ("finisher") adds the partial accumulators its lower-indexed neighbours wrote
 // at the START of their own walk.  A CTA therefore only ever waits for lower-indexed CTAs (no co-residency assumption),
@@ -136,25 +136,34 @@ struct Sched {
     long long u0, seg_end;      // stream-K unit range [u0, seg_end) still to do (units = k-iterations)
     int ipt;                    // k-iterations per tile
     int dp_next, dp_waves, G, c, T_sk;
-    __device__ __forceinline__ void init(long long U_sk, int ipt_, int T_sk_, int dp_waves_, int G_, int c_) {
-        ipt = ipt_; T_sk = T_sk_; dp_waves = dp_waves_; G = G_; c = c_; dp_next = 0;
+    bool dp_first;
+    __device__ __forceinline__ void init(long long U_sk, int ipt_, int T_sk_, int dp_waves_, int G_, int c_,
+                                         bool dp_first_) {
+        ipt = ipt_; T_sk = T_sk_; dp_waves = dp_waves_; G = G_; c = c_; dp_next = 0; dp_first = dp_first_;
         u0 = U_sk * c / G; seg_end = U_sk * (c + 1) / G;
     }
     // next segment: k-iterations [it0, it1) of tile `tile`
+    // whole tiles (data-parallel waves)
+    __device__ __forceinline__ bool next_dp(int& tile, int& it0, int& it1) {
+        if (dp_next >= dp_waves) return false;
+        tile = T_sk + dp_next * G + c; it0 = 0; it1 = ipt; ++dp_next;
+        return true;
+    }
+    // this CTA's stream-K range, from its end backwards
+    __device__ __forceinline__ bool next_sk(int& tile, int& it0, int& it1) {
+        if (seg_end <= u0) return false;
+        tile = (int)((seg_end - 1) / ipt);
+        const long long tb = (long long)tile * ipt;
+        const long long b = u0 > tb ? u0 : tb;
+        it0 = (int)(b - tb); it1 = (int)(seg_end - tb);
+        seg_end = b;
+        return true;
+    }
+    // Stream-K first hides the fix-up wait behind the whole tiles that follow; the arrival-gated matvec instead
+    // wants whole tiles first (they start at k = 0, i.e. with the block that is already local).
     __device__ __forceinline__ bool next(int& tile, int& it0, int& it1) {
-        if (dp_next < dp_waves) {           // whole tiles first (they start at k = 0: the gated matvec wants that)
-            tile = T_sk + dp_next * G + c; it0 = 0; it1 = ipt; ++dp_next;
-            return true;
-        }
-        if (seg_end > u0) {                 // then this CTA's stream-K range, from its end backwards
-            tile = (int)((seg_end - 1) / ipt);
-            const long long tb = (long long)tile * ipt;
-            const long long b = u0 > tb ? u0 : tb;
-            it0 = (int)(b - tb); it1 = (int)(seg_end - tb);
-            seg_end = b;
-            return true;
-        }
-        return false;
+        if (dp_first) return next_dp(tile, it0, it1) || next_sk(tile, it0, it1);
+        return next_sk(tile, it0, it1) || next_dp(tile, it0, it1);
     }
 };
 
@@ -204,7 +213,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 
     // ---- producer (thread 0): walks the same segment sequence as the consumers, S-2 stages ahead
     constexpr int KMUL = CPLX ? 2 : 1;       // innermost TMA coordinate is in float64 units
-    Sched ps; ps.init(sk.U_sk, sk.ipt, sk.T_sk, sk.dp_waves, G, cta);
+    Sched ps; ps.init(sk.U_sk, sk.ipt, sk.T_sk, sk.dp_waves, G, cta, g.ksplit > 1);
     int p_tile = -1, p_it = 0, p_it1 = 0, p_m0 = 0, p_n0 = 0, p_z = 0;
     int pj = 0;                              // CTA-local index of the next k-iteration to issue
     int p_chunk_ok = -1;                     // last gated k chunk known to have arrived
@@ -251,7 +260,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     FragAddr<CPLX, A_KC> fa; fa.init(wm0, g8, t4);
     FragAddr<CPLX, B_KC> fb; fb.init(wn0, g8, t4);
 
-    Sched cs; cs.init(sk.U_sk, sk.ipt, sk.T_sk, sk.dp_waves, G, cta);
+    Sched cs; cs.init(sk.U_sk, sk.ipt, sk.T_sk, sk.dp_waves, G, cta, g.ksplit > 1);
     int tile, it0, it1;
     int cj = 0;                              // CTA-local index of the k-iteration being consumed
     double* my_partial = sk.partial + (size_t)cta * kAccPerThread * kTmaThreads + tid;
