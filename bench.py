@@ -456,6 +456,22 @@ def extras(args, qsb, _lib, dev, dtype, L, M1, M2, R, theta, peak_tf):
         torch.cuda.empty_cache()
     except Exception as ex:
         out["bond_step"] = {"error": repr(ex)[:200]}
+    # (3c) the stock-builder flavour of the same config: complex128 MPO (Sx, Sy, Sz), same chi
+    try:
+        if dtype == torch.float64:
+            Lc, M1c, M2c, Rc, thc = make_inputs(chi, torch.complex128, dev)
+            outc = torch.empty_like(thc)
+            for _ in range(2):
+                op(thc, Lc, M1c, M2c, Rc, out=outc)
+            s = time_region(lambda: op(thc, Lc, M1c, M2c, Rc, out=outc), 5) / 5
+            fc = _lib.heff_flops(thc, Lc, M1c, M2c, Rc)
+            out["complex128_same_config"] = {"gflops": fc / s / 1e9, "ms": s * 1e3,
+                                             "frac_of_fp64_tensor_peak": fc / s / 1e12 / peak_tf,
+                                             "note": "Heisenberg1DMPOBuilder-style complex MPO; 8 flop per complex MAC"}
+            del Lc, Rc, thc, outc
+            torch.cuda.empty_cache()
+    except Exception as ex:
+        out["complex128_same_config"] = {"error": repr(ex)[:200]}
     # (4) CPU baseline: the oracle on the host cores, bounded sample of the same workload
     cores = os.cpu_count() or 1
     try:

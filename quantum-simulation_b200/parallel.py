@@ -287,7 +287,8 @@ class ShardedDMRG:
         tensors (a replicated cuSOLVER call is not guaranteed to be bit-reproducible across devices).
     """
 
-    def __init__(self, mps, mpo, *, device, dtype=torch.float64, group=None, min_shard_chi: int = 64, engine=None):
+    def __init__(self, mps, mpo, *, device, dtype=torch.float64, group=None, min_shard_chi: int = 64, engine=None,
+                 use_fused: bool = True):
         import torch.distributed as dist
         from .dmrg import _as_mpo_list, _check_mpo_shapes
         self.group = group if group is not None else dist.group.WORLD
@@ -304,6 +305,8 @@ class ShardedDMRG:
         self.min_shard_chi = int(min_shard_chi)
         self.engine = engine if engine is not None else CudaEngine()
         self.history = self._empty_history()
+        self.use_fused = bool(use_fused)
+        self._ops_cache: dict = {}
         self.comm = {"all_gather_vec": 0, "all_gather_env": 0, "reduce_scatter_env": 0, "all_reduce_env": 0,
                      "broadcast_split": 0, "sharded_steps": 0, "replicated_steps": 0}
 
@@ -378,7 +381,7 @@ class ShardedDMRG:
         per_row = M1.shape[3] * M2.shape[3] * R_full.shape[2]
         if L.sharded:
             lo, hi = self._block(chi_l)
-            op = ShardedApplyMPO(chi_l, per_row, group=self.group, local_op=self.engine.apply_mpo)
+            op = self._sharded_op(chi_l, per_row, theta.dtype, theta.device)
             shard = theta.reshape(-1)[lo * per_row: hi * per_row]
             v, E = lanczos_ground_state_sharded(shard, op, (L.t, M1, M2, R_full), group=self.group,
                                                 _vector_ops=self.engine.vector_ops, **kw)
@@ -388,6 +391,22 @@ class ShardedDMRG:
         self.comm["replicated_steps"] += 1
         v, E = self.engine.lanczos(theta.reshape(-1), self.engine.apply_mpo, (L.t, M1, M2, R_full), **kw)
         return v, E
+
+    def _sharded_op(self, chi_l: int, per_row: int, dtype, device):
+        """The sharded matvec for this bond: the fused P2P-push + gated-GEMM operator when the bond allows it (CUDA
+        engine, chi_l divisible by BK * world), else all-gather + local matvec.  Cached per shape: building the fused
+        operator allocates symmetric memory and is a collective, which every rank reaches in the same order."""
+        key = (chi_l, per_row, dtype)
+        op = self._ops_cache.get(key)
+        if op is None:
+            bk = 8 if dtype.is_complex else 16
+            if self.use_fused and isinstance(self.engine, CudaEngine) and chi_l % (bk * self.world) == 0:
+                op = FusedShardedApplyMPO(chi_l, per_row, dtype, device, group=self.group)
+                self.comm["fused_ops_built"] = self.comm.get("fused_ops_built", 0) + 1
+            else:
+                op = ShardedApplyMPO(chi_l, per_row, group=self.group, local_op=self.engine.apply_mpo)
+            self._ops_cache[key] = op
+        return op
 
     def _split(self, theta2d: torch.Tensor, chi: int, cutoff: float):
         """Two-site split on rank 0, factors broadcast to everyone."""

@@ -143,6 +143,28 @@ def test_matvec_vs_oracle_seeded(dtype, mk, chi_l, chi_r, layout):
     assert rel_err(out, ref) <= TOL
 
 
+@pytest.mark.parametrize("dtype,mk,chi", [(torch.float64, "j1j2_f64_8x6", 512), (torch.complex128, "hubbard_f64_L64", 320),
+                                          (torch.float64, "hubbard_f64_L64", 512), (torch.complex128, "tfim_c128_L100_g0.5", 768)])
+def test_matvec_config45_shapes_vs_oracle_on_device(dtype, mk, chi):
+    """BASELINE configs 4/5 MPOs (J1-J2 cylinder W~30-38, Hubbard d=4) at bond dimensions the CPU oracle cannot do
+    in seconds: the oracle's tensordot chain executed by cuBLAS on the same device is the checker."""
+    mpo = golden_mpo(mk, dtype, DEV)
+    p = len(mpo) // 2
+    M1, M2 = mpo[p], mpo[p + 1]
+    g = torch.Generator(device=DEV).manual_seed(17)
+    L = torch.randn(M1.shape[0], chi, chi, dtype=dtype, device=DEV, generator=g)
+    R = torch.randn(M2.shape[1], chi, chi, dtype=dtype, device=DEV, generator=g)
+    x = torch.randn(chi * M1.shape[3] * M2.shape[3] * chi, dtype=dtype, device=DEV, generator=g)
+    out = qsb.ApplyMPO()(x, L, M1, M2, R)
+    ref = orc.apply_mpo(x, L, M1, M2, R)
+    assert rel_err(out, ref) <= TOL
+    A = torch.randn(chi, M1.shape[2], chi, dtype=dtype, device=DEV, generator=g)
+    assert rel_err(qsb.LeftEnvUpdate()(L, M1, A), orc.left_env_update(L, M1, A)) <= TOL
+    assert rel_err(qsb.RightEnvUpdate()(M2, R, A), orc.right_env_update(M2, R, A)) <= TOL
+    del out, ref
+    torch.cuda.empty_cache()
+
+
 def test_matvec_arbitrary_strides_and_views():
     """L / R given as slices of bigger tensors (neither inner stride is 1) are canonicalised, not rejected."""
     dtype = torch.float64
