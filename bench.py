@@ -316,15 +316,29 @@ def run_ours(args):
                 "step4_tflops": g4_flops / (sum(g4) / K * 1e-3) / 1e12,
                 "matvec_frac_of_peak": (flops_local / (ms_step * 1e-3) / 1e12) / peak_tf if peak_tf else None}
 
-    # ---- e2e: ApplyMPO.forward with theta in pinned host memory, H2D + D2H inside the timed region
-    h_theta = torch.empty(n, dtype=dtype).pin_memory()
-    h_theta.copy_(theta.cpu())
+    # ---- e2e: the public call with the step's input in pinned HOST memory and the result read back to the host,
+    # both copies inside the timed region.  N > 1: every rank uploads ITS shard of theta (the sharded operator's
+    # input), the exchange happens on the devices, every rank downloads its rows of the result.
     h_out = torch.empty(n_loc, dtype=dtype).pin_memory()
-    d_theta = torch.empty_like(theta)
+    if world == 1:
+        h_in = torch.empty(n, dtype=dtype).pin_memory()
+        h_in.copy_(theta.cpu())
+        d_in = torch.empty_like(theta)
+    else:
+        h_in = torch.empty(n // world, dtype=dtype).pin_memory()
+        h_in.copy_(theta_shard.cpu())
+        d_in = torch.empty_like(theta_shard)
 
     def step_e2e():
-        d_theta.copy_(h_theta, non_blocking=True)
-        op(d_theta, L, M1, M2, R, out=out)
+        d_in.copy_(h_in, non_blocking=True)
+        if fused is not None:
+            fused(d_in, L, M1, M2, R, out=out)
+        else:
+            if world > 1:
+                dist.all_gather_into_tensor(theta, d_in)
+                op(theta, L, M1, M2, R, out=out)
+            else:
+                op(d_in, L, M1, M2, R, out=out)
         h_out.copy_(out, non_blocking=True)
 
     for _ in range(2):
@@ -338,8 +352,11 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         sec_e = float(t.item())
     e2e = {"value": flops_total / (sec_e / Ke) / 1e9, "unit": UNIT, "h2d_bytes_per_step": n * es,
-           "d2h_bytes_per_step": n_loc * es, "ms_per_step": sec_e / Ke * 1e3, "steps": Ke,
-           "call": "quantum_simulation_b200.ApplyMPO.forward (torch.ops.qsb200.heff_apply -> qsb_heff_apply)"}
+           "d2h_bytes_per_step": n * es, "ms_per_step": sec_e / Ke * 1e3, "steps": Ke,
+           "bytes_note": "whole-job bytes per step, summed over ranks (each rank moves 1/N of them)",
+           "call": ("quantum_simulation_b200.ApplyMPO.forward" if world == 1 else
+                    "quantum_simulation_b200.parallel.FusedShardedApplyMPO / ShardedApplyMPO")
+                   + " (torch.ops.qsb200.heff_apply* -> qsb_heff_apply)"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
