@@ -168,12 +168,12 @@ __global__ void __launch_bounds__(kLzThreads) lz_axpy_norm_kernel(const T* X, lo
 template <typename T, int MODE>
 __global__ void __launch_bounds__(kLzThreads) lz_scale_kernel(const T* src, T* dst, long long nunits,
                                                               const double* scal, int idx) {
-    const double s = scal[2 * idx];
+    const double inv = 1.0 / scal[2 * idx];      // one division; the stream multiplies (<= 1.5 ulp from x / s)
     const long long stride = (long long)gridDim.x * kLzThreads;
 #pragma unroll 4
     for (long long u = (long long)blockIdx.x * kLzThreads + threadIdx.x; u < nunits; u += stride) {
         Unit<T, MODE> x = Unit<T, MODE>::load(src, u);
-        x.a /= s; x.b /= s;
+        x.a *= inv; x.b *= inv;
         x.store(dst, u);
     }
 }
