@@ -266,11 +266,13 @@ template <bool CPLX, bool A_KC, bool B_KC, int VEC>
 static int launch_cpasync(const KArgs& k, int Z, cudaStream_t stream) {
     auto kern = gemm_cpasync<CPLX, A_KC, B_KC, VEC>;
     constexpr int SMEM = kStages * stage_bytes<CPLX>();
-    static bool configured = false;          // per instantiation
-    if (!configured) {
+    static bool configured[64] = {};         // per instantiation and device (the attribute is per device)
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return QSB_ERR_DEVICE;
+    if (!configured[dev]) {
         int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         if (rc) return rc;
-        configured = true;
+        configured[dev] = true;
     }
     const long long blocks = (long long)k.tiles_m * k.tiles_n * Z;
     if (blocks <= 0) return QSB_OK;

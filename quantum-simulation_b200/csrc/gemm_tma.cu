@@ -515,11 +515,13 @@ static int launch_tma(const CUtensorMap& ma, const CUtensorMap& mb, const TArgs&
     using C = TCfg<CPLX>;
     auto kern = gemm_tma_kernel<CPLX, A_KC, B_KC>;
     constexpr int SMEM = C::STAGES * (C::BM + C::BN) * C::BK * C::ES + 2 * C::STAGES * 8 + 1024;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};         // per instantiation and device (the attribute is per device)
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return QSB_ERR_DEVICE;
+    if (!configured[dev]) {
         int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         if (rc) return rc;
-        configured = true;
+        configured[dev] = true;
     }
     SkScratch* sc = nullptr;
     int rc = sk_scratch(&sc);
