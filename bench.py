@@ -394,6 +394,13 @@ def extras(args, qsb, _lib, dev, dtype, L, M1, M2, R, theta, peak_tf):
         s = time_region(lambda: orc.apply_mpo(theta, L, M1, M2, R), 5) / 5
         out["torch_cublas_same_matvec"] = {"gflops": flops / s / 1e9, "ms": s * 1e3,
                                            "what": "oracle tensordot chain on device='cuda' (cuBLAS + permute copies)"}
+        # the reference's contract_backend='auto' resolves to its einsum branch on CUDA (dmrg.py:101-102, 230-248):
+        # O(W_l W_r d^2 chi^3) -- what a user of the stock reference gets on this GPU today
+        orc.apply_mpo_einsum(theta, L, M1, M2, R)
+        s = time_region(lambda: orc.apply_mpo_einsum(theta, L, M1, M2, R), 2) / 2
+        out["torch_einsum_auto_backend_same_matvec"] = {"gflops_dense_equivalent": flops / s / 1e9, "ms": s * 1e3,
+                                                        "what": "oracle restatement of the reference's einsum branch "
+                                                                "on device='cuda'"}
         torch.cuda.empty_cache()
     except Exception as ex:          # library leg is informational only
         out["library_leg_error"] = repr(ex)[:200]
