@@ -19,7 +19,7 @@ import torch
 from .eigensolver import _lanczos_impl, _CUDA_OPS
 
 __all__ = ["row_partition", "ShardedApplyMPO", "lanczos_ground_state_sharded", "shard_rows", "gather_rows",
-           "ShardedDMRG", "CudaEngine", "FusedShardedApplyMPO"]
+           "ShardedDMRG", "CudaEngine", "FusedShardedApplyMPO", "SymmetricArena"]
 
 
 def row_partition(chi: int, world: int) -> List[Tuple[int, int]]:
@@ -105,6 +105,37 @@ class ShardedApplyMPO:
         return self.local_op(full, L_rows, M1, M2, R, out=out)
 
 
+class SymmetricArena:
+    """One peer-mapped (``torch.distributed._symmetric_memory``) allocation shared by every fused operator of a
+    process group: [flags (256 B)] [gathered buffer 0] [gathered buffer 1].  Allocating and rendezvous-ing symmetric
+    memory is a slow collective, so a sweep does it once for the largest bond instead of once per bond shape.  The
+    epoch counter is shared too (flags are monotonic per source rank)."""
+
+    def __init__(self, max_vector_bytes: int, device, group: Any = None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.stride = (int(max_vector_bytes) + 255) // 256 * 256
+        total = 256 + 2 * self.stride
+        try:
+            symm_mem.enable_symm_mem_for_group(self.group.group_name)
+        except Exception:
+            pass
+        self.store = symm_mem.empty(total, dtype=torch.uint8, device=device)
+        self.store.zero_()
+        torch.cuda.synchronize(device)
+        self.hdl = symm_mem.rendezvous(self.store, self.group.group_name)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.flags = self.store[:256].view(torch.int32)
+        self.flag_ptrs = [self.ptrs[r] + 4 * self.rank for r in range(self.world)]
+        self.ticket = torch.zeros(1, dtype=torch.int32, device=device)
+        self.side = [torch.cuda.Stream(device=device) for _ in range(2)]
+        self.epoch = 0
+        dist.barrier(group=self.group)
+
+
 class FusedShardedApplyMPO:
     """Sharded H_eff . theta with the all-gather FUSED into the matvec (no NCCL call on the data path).
 
@@ -117,54 +148,51 @@ class FusedShardedApplyMPO:
     parity, flags are monotonic epochs, so a rank that runs one step ahead never overwrites data a peer still reads.
     """
 
-    def __init__(self, chi_l: int, per_row: int, dtype: torch.dtype, device, group: Any = None, push: str = "dma"):
+    def __init__(self, chi_l: int, per_row: int, dtype: torch.dtype, device, group: Any = None, push: str = "dma",
+                 arena: Optional[SymmetricArena] = None):
         import torch.distributed as dist
-        import torch.distributed._symmetric_memory as symm_mem
         from . import _lib
         self._ops = _lib.ops
         self._lib = _lib
         if push not in ("dma", "sm"):
-            raise ValueError("push must be 'dma' (copy engines on a side stream) or 'sm' (one store kernel)")
+            raise ValueError("push must be 'dma' (copy engines on side streams) or 'sm' (one store kernel)")
         self.push = push
-        self._side = [torch.cuda.Stream(device=device) for _ in range(2)] if push == "dma" else []
-        self.group = group if group is not None else dist.group.WORLD
-        self.world = dist.get_world_size(self.group)
-        self.rank = dist.get_rank(self.group)
+        grp = group if group is not None else dist.group.WORLD
+        world = dist.get_world_size(grp)
         es = torch.empty(0, dtype=dtype).element_size()
         bk = 8 if dtype.is_complex else 16
-        if chi_l % self.world != 0 or (chi_l // bk) % self.world != 0 or chi_l % bk != 0:
+        if chi_l % world != 0 or (chi_l // bk) % world != 0 or chi_l % bk != 0:
             raise ValueError(f"fused sharded matvec needs chi_l divisible by {bk} * world_size (got chi_l={chi_l}, "
-                             f"world={self.world}); use ShardedApplyMPO")
+                             f"world={world}); use ShardedApplyMPO")
+        n = chi_l * per_row
+        if arena is None:
+            arena = SymmetricArena(n * es, device, grp)
+        elif arena.stride < n * es:
+            raise ValueError("symmetric arena too small for this bond")
+        self.arena = arena
+        self.group, self.world, self.rank = arena.group, arena.world, arena.rank
         self.chi_l, self.per_row = chi_l, per_row
         self.lo, self.hi = row_partition(chi_l, self.world)[self.rank]
-        n = chi_l * per_row
         shard_bytes = (n // self.world) * es
-        stride = (n * es + 255) // 256 * 256
-        total = 256 + 2 * stride
-        try:
-            symm_mem.enable_symm_mem_for_group(self.group.group_name)
-        except Exception:
-            pass
-        self._store = symm_mem.empty(total, dtype=torch.uint8, device=device)
-        self._store.zero_()
-        torch.cuda.synchronize(device)
-        self._hdl = symm_mem.rendezvous(self._store, self.group.group_name)
-        ptrs = [int(p) for p in self._hdl.buffer_ptrs]
-        self.flags = self._store[:256].view(torch.int32)
-        self.bufs = [self._store[256 + b * stride: 256 + b * stride + n * es].view(dtype) for b in (0, 1)]
-        self.dst_ptrs = [[ptrs[r] + 256 + b * stride + self.rank * shard_bytes for r in range(self.world)]
+        st = arena.stride
+        self.flags = arena.flags
+        self.bufs = [arena.store[256 + b * st: 256 + b * st + n * es].view(dtype) for b in (0, 1)]
+        self.dst_ptrs = [[arena.ptrs[r] + 256 + b * st + self.rank * shard_bytes for r in range(self.world)]
                          for b in (0, 1)]
-        self.flag_ptrs = [ptrs[r] + 4 * self.rank for r in range(self.world)]
-        self.ticket = torch.zeros(1, dtype=torch.int32, device=device)
-        self.epoch = 0
+        self.flag_ptrs = arena.flag_ptrs
+        self.ticket = arena.ticket
+        self._side = arena.side if push == "dma" else []
         # push order: own block, then rank-1, rank-2, ...  Rank m therefore RECEIVES blocks m+1, m+2, ... in that
         # order -- the order in which its gated GEMM walks the k chunks (rotation starts at its own block).
         self._order = [(self.rank - i) % self.world for i in range(self.world)]
-        dist.barrier(group=self.group)
+
+    @property
+    def epoch(self) -> int:
+        return self.arena.epoch
 
     def __call__(self, v_shard, L_rows, M1, M2, R, out=None):
-        self.epoch += 1
-        b = self.epoch & 1
+        self.arena.epoch += 1
+        b = self.arena.epoch & 1
         v = v_shard.reshape(-1)
         if not v.is_contiguous():
             v = v.contiguous()
@@ -307,6 +335,10 @@ class ShardedDMRG:
         self.history = self._empty_history()
         self.use_fused = bool(use_fused)
         self._ops_cache: dict = {}
+        self._arena: Optional[SymmetricArena] = None
+        self._max_chi = 0
+        self.profile = False            # True: synchronise around the phases and accumulate seconds in self.timers
+        self.timers = {"theta": 0.0, "gather_R": 0.0, "lanczos": 0.0, "split": 0.0, "env": 0.0}
         self.comm = {"all_gather_vec": 0, "all_gather_env": 0, "reduce_scatter_env": 0, "all_reduce_env": 0,
                      "broadcast_split": 0, "sharded_steps": 0, "replicated_steps": 0}
 
@@ -401,7 +433,13 @@ class ShardedDMRG:
         if op is None:
             bk = 8 if dtype.is_complex else 16
             if self.use_fused and isinstance(self.engine, CudaEngine) and chi_l % (bk * self.world) == 0:
-                op = FusedShardedApplyMPO(chi_l, per_row, dtype, device, group=self.group)
+                es = torch.empty(0, dtype=dtype).element_size()
+                if self._arena is None or self._arena.stride < chi_l * per_row * es:
+                    # one symmetric allocation for the largest vector this run can see (maxdim^2 d^2)
+                    big = max(chi_l * per_row, self._max_chi * self._max_chi * self.chid * self.chid)
+                    self._arena = SymmetricArena(big * es, device, self.group)
+                    self.comm["arenas_built"] = self.comm.get("arenas_built", 0) + 1
+                op = FusedShardedApplyMPO(chi_l, per_row, dtype, device, group=self.group, arena=self._arena)
                 self.comm["fused_ops_built"] = self.comm.get("fused_ops_built", 0) + 1
             else:
                 op = ShardedApplyMPO(chi_l, per_row, group=self.group, local_op=self.engine.apply_mpo)
@@ -438,6 +476,10 @@ class ShardedDMRG:
         sites = range(N - 1) if direction == "right" else range(N - 2, -1, -1)
         kw = dict(num_restarts=params["maxit"], krylov_dim=params["krydim"], pro=params["reortho"],
                   pro_max_reorth=params["maxreortho"])
+        if self.profile:
+            import time
+            torch.cuda.synchronize()
+            self._t_last = time.perf_counter()
         for p in sites:
             if direction == "right":                                  # theta build, replicated (dmrg.py:633-646)
                 lt, rt, sw = B[p], B[p + 1], sW[p]
@@ -454,11 +496,15 @@ class ShardedDMRG:
                 _m, t, r = rt.shape
                 psi = torch.matmul(lt.reshape(l * s, m), torch.mul(rt, sw.to(rt.dtype).view(1, 1, -1)).reshape(m, t * r))
             chil, chir = l, r
+            self._tick("theta")
             R_full = self._full(R[p + 2])
+            self._tick("gather_R")
             theta, E = self._ground_state(psi, L[p], self.Ms[p], self.Ms[p + 1], R_full, chil, kw)
+            self._tick("lanczos")
             Ekeep.append(E)
             self.history["energies"].append(float(E))
             Uk, S, Vhk, keep = self._split(theta.reshape(chil * d, d * chir), params["chi"], params["cutoff"])
+            self._tick("split")
             self.history["discarded_weights"].append(torch.sum(S[keep:] ** 2).real.item())
             self.history["bond_dims"].append(int(keep))
             self.history["sweeps"].append(int(params["sweep_idx"]))
@@ -473,8 +519,18 @@ class ShardedDMRG:
                 L[p + 1] = self._update_L(L[p], self.Ms[p], A[p])
             else:
                 R[p + 1] = self._update_R(self.Ms[p + 1], R_full, B[p + 1])
+            self._tick("env")
             if params["dispon"] == 2 and self.rank == 0:
                 print(f"Sweep: {params['sweep_idx']} of {params['numsweeps']}, Loc: {p}, Energy: {Ekeep[-1]:.6f}")
+
+    def _tick(self, phase: str) -> None:
+        if not self.profile:
+            return
+        import time
+        torch.cuda.synchronize()
+        now = time.perf_counter()
+        self.timers[phase] += now - self._t_last
+        self._t_last = now
 
     def _boundary(self, mat: torch.Tensor):
         """Small boundary SVD (dmrg.py:776, 793): rank 0 computes, everyone receives the same factors."""
@@ -493,6 +549,7 @@ class ShardedDMRG:
         N, d = self.Nsites, self.chid
         Ekeep: list = []
         self.history = self._empty_history()
+        self._max_chi = max(int(x) for x in sweeps.maxdim)
         L: list = [None] * (N + 1)
         R: list = [None] * (N + 1)
         L[0] = _Env(torch.ones(self.Ms[0].shape[0], 1, 1, device=self.device, dtype=self.dtype), False, 1)

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--L", type=int, default=40)
     ap.add_argument("--chi", type=int, default=1024)
     ap.add_argument("--dtype", default="f64")
+    ap.add_argument("--profile", action="store_true")
     args = ap.parse_args()
     rank, world, local = bench.dist_setup(0)
     dev = torch.device("cuda", local)
@@ -54,6 +55,7 @@ def main():
     qsb.clear_workspaces()
     torch.cuda.empty_cache()
     d2 = parallel.ShardedDMRG(m2, mpo, device=dev, dtype=dtype)
+    d2.profile = args.profile
     dist.barrier()
     t0 = time.perf_counter()
     Ed, _ = d2(sched(), dispon=0)
@@ -67,7 +69,8 @@ def main():
                           "world": world, "sweep_s_single_gpu": t_single, "sweep_s_sharded": t_shard,
                           "speedup": t_single / t_shard, "E_end_single": float(Es[-1]), "E_end_sharded": float(Ed[-1]),
                           "rel_dev_end_of_sweep": float(rel[-1]), "max_rel_dev_updates_after_20": float(rel[20:].max()),
-                          "bond_dims_equal": d1.history["bond_dims"] == d2.history["bond_dims"], "comm": d2.comm}))
+                          "bond_dims_equal": d1.history["bond_dims"] == d2.history["bond_dims"], "comm": d2.comm,
+                          "phase_seconds_rank0": d2.timers if args.profile else None}))
     dist.destroy_process_group()
 
 
