@@ -102,7 +102,8 @@ int qsb_push_shard(const void* src, size_t bytes, void* const* dst, int* const* 
                    void* ticket, void* stream);
 /* Same contract on the copy engines: for each of the `count` destinations, in the given order, one peer
    cudaMemcpyAsync followed by one stream-ordered 32-bit flag write (cuStreamWriteValue32).  No SM is used, so on a
-   side stream it overlaps the persistent GEMM of the matvec that consumes the blocks. */
+   side stream it overlaps the persistent GEMM of the matvec that consumes the blocks.  `src` may also be PINNED HOST
+   memory (cudaMemcpyDefault): the same gating then overlaps a host->device upload of theta with the step-1 GEMM. */
 int qsb_push_shard_dma(const void* src, size_t bytes, void* const* dst, int* const* flag, int count, int epoch,
                        void* stream);
 

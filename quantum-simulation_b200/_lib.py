@@ -265,8 +265,14 @@ def _impl_push_shard(src, dst_ptrs: Sequence[int], flag_ptrs: Sequence[int], epo
 
 
 def push_shard_dma(src: torch.Tensor, dst_ptrs: Sequence[int], flag_ptrs: Sequence[int], epoch: int) -> None:
-    """Copy-engine push, destinations in the given order, on the CURRENT stream (callers use side streams)."""
-    dev = _require_cuda(src)
+    """Copy-engine push, destinations in the given order, on the CURRENT stream (callers use side streams).
+    ``src`` is a CUDA tensor or a pinned host tensor."""
+    if src.device.type == "cuda":
+        dev = src.device
+    else:
+        if not src.is_pinned():
+            raise ValueError("push_shard_dma: a host source must be pinned memory")
+        dev = torch.device("cuda", torch.cuda.current_device())
     world = len(dst_ptrs)
     dp = (C.c_void_p * world)(*[C.c_void_p(int(p)) for p in dst_ptrs])
     fp = (C.c_void_p * world)(*[C.c_void_p(int(p)) for p in flag_ptrs])

@@ -491,7 +491,7 @@ extern "C" int qsb_push_shard_dma(const void* src, size_t bytes, void* const* ds
     cudaStream_t stream = (cudaStream_t)stream_;
     for (int i = 0; i < count; ++i) {                 // in the caller's order
         if (!dst[i] || !flag[i]) return QSB_ERR_ARG;
-        int rc = check_cuda(cudaMemcpyAsync(dst[i], src, bytes, cudaMemcpyDeviceToDevice, stream));
+        int rc = check_cuda(cudaMemcpyAsync(dst[i], src, bytes, cudaMemcpyDefault, stream));   // peer, local or pinned host source
         if (rc) return rc;
         if (wv((CUstream)stream, (CUdeviceptr)flag[i], (cuuint32_t)epoch, 0) != CUDA_SUCCESS) return QSB_ERR_LAUNCH;
     }

@@ -102,6 +102,8 @@ class ApplyMPO(_BaseContractModule):
 
     def forward(self, psi_flat: torch.Tensor, L: torch.Tensor, M1: torch.Tensor, M2: torch.Tensor,
                 R: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if psi_flat.device.type == "cpu" and L.device.type == "cuda":
+            return self._forward_host(psi_flat, L, M1, M2, R, out)
         psi, L, M1, M2, R = (_dev_tensor(t) for t in (psi_flat, L, M1, M2, R))
         if not psi.is_contiguous():
             psi = psi.contiguous()
@@ -122,6 +124,94 @@ class ApplyMPO(_BaseContractModule):
             res = torch.empty(n_out, device=psi.device, dtype=psi.dtype)
         _lib.ops.heff_apply(psi.view(-1), L, M1, M2, R, res)
         return res
+
+
+    # ---- host-resident vector, device-resident operator ---------------------------------------------------
+    _host_pipes: dict = {}
+
+    def _forward_host(self, psi_host: torch.Tensor, L, M1, M2, R, out_host: Optional[torch.Tensor]) -> torch.Tensor:
+        """``psi_flat`` (and ``out``) in PINNED HOST memory, L / M / R on the GPU: the upload of theta, the matvec
+        and the download of the result are pipelined instead of serialised.  theta goes up in k-chunks on a copy
+        stream, each followed by a stream-ordered flag write, and the step-1 GEMM is gated per chunk (the same
+        mechanism as the multi-GPU fused exchange); the matvec runs in row blocks of the left bond and each finished
+        block is downloaded on a second copy stream while the next one computes.  Compute stays on the GPU -- this is
+        not a CPU fallback; unpinned host tensors are rejected."""
+        L, M1, M2, R = (_dev_tensor(t) for t in (L, M1, M2, R))
+        M1, M2 = M1.contiguous(), M2.contiguous()
+        dev = L.device
+        psi_host = psi_host.reshape(-1)
+        if not psi_host.is_pinned() or not psi_host.is_contiguous():
+            raise ValueError("[ApplyMPO] a host-resident psi_flat must be contiguous pinned memory")
+        dt = psi_host.dtype
+        chi_lo, chi_li = L.shape[1], L.shape[2]
+        n_in = chi_li * M1.shape[3] * M2.shape[3] * R.shape[2]
+        per_out = M1.shape[2] * M2.shape[2] * R.shape[1]
+        n_out = chi_lo * per_out
+        if psi_host.numel() != n_in:
+            raise AssertionError(f"[ApplyMPO] psi has {psi_host.numel()} elements, the operator expects {n_in}")
+        if out_host is None:
+            out_host = torch.empty(n_out, dtype=dt).pin_memory()
+        if out_host.numel() != n_out or out_host.dtype != dt or out_host.device.type != "cpu" \
+                or not out_host.is_pinned() or not out_host.is_contiguous():
+            raise ValueError("[ApplyMPO] out shape/device/dtype mismatch.")
+        pipe = ApplyMPO._host_pipes.get(dev)
+        if pipe is None:
+            pipe = {"flags": torch.zeros(64, dtype=torch.int32, device=dev), "epoch": 0,
+                    "h2d": torch.cuda.Stream(device=dev), "d2h": torch.cuda.Stream(device=dev), "theta": None,
+                    "out": None}
+            ApplyMPO._host_pipes[dev] = pipe
+        for key, numel in (("theta", n_in), ("out", n_out)):
+            buf = pipe[key]
+            if buf is None or buf.numel() < numel or buf.dtype != dt:
+                pipe[key] = torch.empty(numel, dtype=dt, device=dev)
+        theta_dev, out_dev = pipe["theta"][:n_in], pipe["out"][:n_out]
+        bk = 8 if dt.is_complex else 16
+        n_chunks = 8
+        while n_chunks > 1 and (chi_li % (bk * n_chunks) != 0):
+            n_chunks //= 2
+        n_blocks = 4
+        while n_blocks > 1 and (chi_lo % n_blocks != 0 or chi_lo // n_blocks < 128):
+            n_blocks //= 2
+        main = torch.cuda.current_stream(dev)
+        es = psi_host.element_size()
+        with torch.cuda.device(dev):
+            pipe["h2d"].wait_stream(main)                  # the staging buffers are free once earlier work is done
+            pipe["d2h"].wait_stream(main)
+            if n_chunks > 1:
+                pipe["epoch"] += 1
+                epoch = pipe["epoch"]
+                chunk = n_in // n_chunks
+                with torch.cuda.stream(pipe["h2d"]):
+                    for c in range(n_chunks):
+                        _lib.push_shard_dma(psi_host[c * chunk:(c + 1) * chunk],
+                                            [theta_dev.data_ptr() + c * chunk * es],
+                                            [pipe["flags"].data_ptr() + 4 * c], epoch)
+            else:
+                with torch.cuda.stream(pipe["h2d"]):
+                    theta_dev.copy_(psi_host, non_blocking=True)
+                main.wait_stream(pipe["h2d"])
+            rows = chi_lo // n_blocks
+            out_h = out_host.view(-1)
+            for b in range(n_blocks):
+                Lb = L[:, b * rows:(b + 1) * rows, :]
+                ob = out_dev[b * rows * per_out:(b + 1) * rows * per_out]
+                if n_chunks > 1:
+                    try:
+                        _lib.ops.heff_apply_gated(theta_dev, Lb, M1, M2, R, ob, pipe["flags"], n_chunks, 0, epoch)
+                    except ValueError:                     # operands the TMA-staged (gated) GEMM cannot describe
+                        main.wait_stream(pipe["h2d"])
+                        n_chunks = 1
+                        _lib.ops.heff_apply(theta_dev, Lb, M1, M2, R, ob)
+                else:
+                    _lib.ops.heff_apply(theta_dev, Lb, M1, M2, R, ob)
+                done = torch.cuda.Event()
+                done.record(main)
+                pipe["d2h"].wait_event(done)
+                with torch.cuda.stream(pipe["d2h"]):
+                    out_h[b * rows * per_out:(b + 1) * rows * per_out].copy_(ob, non_blocking=True)
+            main.wait_stream(pipe["d2h"])                  # the result is on the host once `main` gets here
+            main.wait_stream(pipe["h2d"])
+        return out_host
 
 
 class LeftEnvUpdate(_BaseContractModule):

@@ -92,7 +92,7 @@ def test_no_cpu_fallback():
     L = torch.ones(1, 1, 1, dtype=torch.float64)
     M = torch.ones(1, 1, 2, 2, dtype=torch.float64)
     with pytest.raises(RuntimeError):          # NotImplementedError is a RuntimeError; never TypeError
-        qsb.ApplyMPO()(torch.ones(4, dtype=torch.float64), L, M, M, L)
+        qsb.ApplyMPO()(torch.ones(4, dtype=torch.float64), L, M, M, L)      # operator on the CPU: no kernel
     with pytest.raises(RuntimeError):
         qsb.lanczos_ground_state(torch.ones(4, dtype=torch.float64), lambda x, A: A @ x, (torch.eye(4, dtype=torch.float64),))
     with pytest.raises(RuntimeError):
