@@ -9,7 +9,7 @@ Parity note (hard part vi): CPU and CUDA generators differ,
 """
 from __future__ import annotations
 
-from typing import Any, List, Optional
+from typing import Any, List, Optional, Tuple
 
 import torch
 import torch.nn as nn
@@ -18,24 +18,28 @@ __all__ = ["MPS", "random_mps"]
 
 
 def random_mps(n_sites: int, d: int, chi: int, *, dtype, device, seed: Optional[int] = None) -> List[torch.Tensor]:
-    """Uniform[0,1) site tensors with bond dims min(chi, d^k, d^(N-k))  (mps.py:154-168)."""
-    gen = None
-    if seed is not None:
-        gen = torch.Generator(device=device).manual_seed(seed)
-
-    def rand(*shape):
-        return torch.rand(*shape, generator=gen, device=device, dtype=dtype)
-
-    tensors = [rand(1, d, min(chi, d))]
-    for k in range(1, n_sites):
-        left = tensors[k - 1].shape[2]
-        right = min(min(chi, left * d), d ** (n_sites - k - 1))
-        tensors.append(rand(left, d, right))
-    return tensors
+    """Site tensors with uniform[0,1) entries; bond k is min(chi, d^k, d^(N-k))  (mps.py:154-168)."""
+    gen = torch.Generator(device=device).manual_seed(seed) if seed is not None else None
+    sites: List[torch.Tensor] = []
+    left = 1
+    for k in range(n_sites):
+        cap_right = d ** (n_sites - k - 1)                  # what the sites to the right can support
+        right = min(chi, left * d, cap_right) if k > 0 else min(chi, d)
+        sites.append(torch.rand(left, d, right, generator=gen, device=device, dtype=dtype))
+        left = right
+    return sites
 
 
-def _as_param(t: torch.Tensor) -> nn.Parameter:
+def _frozen(t: torch.Tensor) -> nn.Parameter:
     return nn.Parameter(t, requires_grad=False)
+
+
+def _absorb_right_factor(site: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """site (l, d, r) = R^T-absorbing split: returns (right-isometric site, the l x l' factor to push left).
+    QR of the transposed (l, d*r) matrix, as the reference does (mps.py:52-56, 124-128)."""
+    l, d, r = site.shape
+    Q, Rf = torch.linalg.qr(site.reshape(l, d * r).T)
+    return Q.T.reshape(Q.shape[1], d, r), Rf.T
 
 
 class MPS(nn.Module):
@@ -44,72 +48,60 @@ class MPS(nn.Module):
     def __init__(self, Nsites: int, chid: int, initial_bond_dim: int, device: Any, dtype: torch.dtype,
                  seed: Optional[int] = None):
         super().__init__()
-        self.Nsites, self.chid, self.device, self.dtype = Nsites, chid, device, dtype
+        self.Nsites, self.chid = Nsites, chid
+        self.device, self.dtype = device, dtype
         self.ortho_center = 0
         print("Initializing MPS as a right-canonical random state...")
-        T = random_mps(Nsites, chid, initial_bond_dim, dtype=dtype, device=device, seed=seed)
-        for p in range(Nsites - 1, 0, -1):                      # QR sweep from the right (mps.py:52-58)
-            chil, d, chir = T[p].shape
-            Q, R = torch.linalg.qr(T[p].reshape(chil, d * chir).T)
-            T[p] = Q.T.reshape(Q.shape[1], d, chir)
-            T[p - 1] = torch.einsum("lsc,ck->lsk", T[p - 1], R.T)
-        T[0] = T[0] / torch.linalg.norm(T[0])
-        self._A = nn.ParameterList([_as_param(t) for t in T])
-        self._B = nn.ParameterList([_as_param(t.clone()) for t in T])
-        self._sWeight = nn.ParameterList([_as_param(torch.ones(1, device=device, dtype=dtype))
-                                          for _ in range(Nsites + 1)])
+        sites = random_mps(Nsites, chid, initial_bond_dim, dtype=dtype, device=device, seed=seed)
+        for p in reversed(range(1, Nsites)):                # right-to-left QR sweep
+            sites[p], carry = _absorb_right_factor(sites[p])
+            sites[p - 1] = torch.einsum("lsc,ck->lsk", sites[p - 1], carry)
+        sites[0] = sites[0] / torch.linalg.norm(sites[0])
+        ones = [torch.ones(1, device=device, dtype=dtype) for _ in range(Nsites + 1)]
+        self._A = nn.ParameterList(_frozen(t) for t in sites)
+        self._B = nn.ParameterList(_frozen(t.clone()) for t in sites)
+        self._sWeight = nn.ParameterList(_frozen(t) for t in ones)
         print(f"Initialization complete. Ortho center at site {self.ortho_center}.")
 
-    @property
-    def A(self) -> nn.ParameterList:
-        return self._A
+    A = property(lambda self: self._A, doc="left-canonical site tensors (ParameterList)")
+    B = property(lambda self: self._B, doc="right-canonical site tensors (ParameterList)")
+    sWeight = property(lambda self: self._sWeight, doc="Schmidt values on the bonds (ParameterList)")
 
-    @property
-    def B(self) -> nn.ParameterList:
-        return self._B
-
-    @property
-    def sWeight(self) -> nn.ParameterList:
-        return self._sWeight
+    def _set_site(self, p: int, t: torch.Tensor) -> None:
+        self._A[p] = _frozen(t)
+        self._B[p] = _frozen(t.clone())
 
     def position(self, site_idx: int) -> None:
-        """Move the orthogonality centre by SVD (rightwards) / QR (leftwards) steps (mps.py:87-145)."""
-        if not (0 <= site_idx < self.Nsites):
+        """Move the orthogonality centre: SVD steps to the right, QR steps to the left (mps.py:87-145)."""
+        if site_idx < 0 or site_idx >= self.Nsites:
             raise ValueError(f"site_idx {site_idx} out of bounds for Nsites={self.Nsites}")
         print(f"\nMoving orthogonality center from {self.ortho_center} to {site_idx}...")
         while self.ortho_center < site_idx:
             p = self.ortho_center
-            chil, d, chir = self._A[p].shape
-            U, S, Vh = torch.linalg.svd(self._A[p].reshape(chil * d, chir), full_matrices=False)
-            self._A[p] = _as_param(U.reshape(chil, d, U.shape[1]))
-            self._B[p] = _as_param(self._A[p].clone())
-            sv = S / torch.linalg.norm(S)
-            self._sWeight[p + 1] = _as_param(sv)
-            nxt = torch.einsum("k,kl,lds->kds", sv.to(Vh.dtype), Vh, self._B[p + 1])
-            self._A[p + 1] = _as_param(nxt)
-            self._B[p + 1] = _as_param(nxt.clone())
-            self.ortho_center += 1
+            l, d, r = self._A[p].shape
+            U, S, Vh = torch.linalg.svd(self._A[p].reshape(l * d, r), full_matrices=False)
+            self._set_site(p, U.reshape(l, d, U.shape[1]))
+            schmidt = S / torch.linalg.norm(S)
+            self._sWeight[p + 1] = _frozen(schmidt)
+            self._set_site(p + 1, torch.einsum("k,kl,lds->kds", schmidt.to(Vh.dtype), Vh, self._B[p + 1]))
+            self.ortho_center = p + 1
         while self.ortho_center > site_idx:
             p = self.ortho_center
-            chil, d, chir = self._A[p].shape
-            Q, R = torch.linalg.qr(self._A[p].reshape(chil, d * chir).T)
-            self._A[p] = _as_param(Q.T.reshape(Q.shape[1], d, chir))
-            self._B[p] = _as_param(self._A[p].clone())
-            prev = torch.einsum("lsc,ck->lsk", self._A[p - 1], R.T)
-            self._A[p - 1] = _as_param(prev)
-            self._B[p - 1] = _as_param(prev.clone())
-            self.ortho_center -= 1
-        norm = torch.linalg.norm(self._A[self.ortho_center])
-        self._A[self.ortho_center].data /= norm
-        self._B[self.ortho_center].data /= norm
+            iso, carry = _absorb_right_factor(self._A[p])
+            self._set_site(p, iso)
+            self._set_site(p - 1, torch.einsum("lsc,ck->lsk", self._A[p - 1], carry))
+            self.ortho_center = p - 1
+        c = self.ortho_center
+        nrm = torch.linalg.norm(self._A[c])
+        self._A[c].data /= nrm
+        self._B[c].data /= nrm
         print(f"Orthogonality center is now at site {self.ortho_center}.")
 
     def to(self, *args, **kwargs):
-        out = super().to(*args, **kwargs)
-        for t in self._A:
-            self.device = t.device
-            break
-        return out
+        moved = super().to(*args, **kwargs)
+        if len(self._A) > 0:
+            self.device = self._A[0].device
+        return moved
 
     def __repr__(self) -> str:
         bonds = [self._A[0].shape[0]] + [t.shape[2] for t in self._A]

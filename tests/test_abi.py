@@ -122,3 +122,32 @@ def test_mps_matches_reference_init():
         sums = np.array([t.detach().abs().sum().item() for t in mps.B])
         assert np.allclose(sums, z[f"{name}/init_abs_sums"], rtol=1e-13, atol=0)
         assert mps.ortho_center == 0 and len(mps.sWeight) == L + 1
+
+
+def test_mps_position_keeps_state_and_canonical_form():
+    import io
+    import contextlib
+    with contextlib.redirect_stdout(io.StringIO()):
+        mps = qsb.MPS(7, 2, 6, "cpu", torch.complex128, seed=9)
+
+        def dense(m):
+            v = m.A[0] if m.ortho_center == 0 else None
+            ts = [m.A[p] if p <= m.ortho_center else m.B[p] for p in range(m.Nsites)]
+            out = ts[0]
+            for t in ts[1:]:
+                out = torch.tensordot(out, t, dims=([out.dim() - 1], [0]))
+            return out.reshape(-1)
+        psi0 = dense(mps)
+        for target in (4, 1, 6, 0):
+            mps.position(target)
+            assert mps.ortho_center == target
+            psi = dense(mps)
+            assert abs(abs(torch.vdot(psi0, psi)) - 1.0) < 1e-12          # same state up to a phase
+            for p in range(target):                                      # left of the centre: left isometries
+                a = mps.A[p].reshape(-1, mps.A[p].shape[2])
+                assert torch.linalg.norm(a.conj().T @ a - torch.eye(a.shape[1], dtype=a.dtype)) < 1e-12
+            for p in range(target + 1, mps.Nsites):                      # right of it: right isometries
+                b = mps.B[p].reshape(mps.B[p].shape[0], -1)
+                assert torch.linalg.norm(b @ b.conj().T - torch.eye(b.shape[0], dtype=b.dtype)) < 1e-12
+    with pytest.raises(ValueError):
+        mps.position(7)
