@@ -39,7 +39,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 NCU_TRAFFIC_STEP1_BYTES = 1.856138e9 + 675.188224e6     # ncu --set full, round 1, chi=2048 f64 step-1 GEMM
-METRIC = "H_eff matvec throughput (DMRG two-site, Heisenberg L=100 bulk bond)"
+METRIC = "H_eff matvec GFLOP/s (two-site DMRG bulk bond; default BASELINE config 3: Heisenberg L=100, chi=2048)"
 UNIT = "GFLOP/s"
 
 
@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chi", type=int, default=2048)
     ap.add_argument("--dtype", default="f64", choices=["f64", "c128"])
+    ap.add_argument("--model", default="heis", choices=sorted(MODELS),
+                    help="which BASELINE config's MPO bond to run (default: config 3, the headline)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "fused", "nccl"],
                     help="N>1: how theta shards are exchanged (auto = fused P2P push if available, else NCCL)")
     ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / lanczos / env / library legs")
@@ -62,12 +64,21 @@ def load_mpo(key, dtype):
     return [torch.from_numpy(z[f"{key}/t{int(u)}"]).to(dtype).contiguous() for u in z[f"{key}/index"]]
 
 
+MODELS = {   # model -> (MPO key for f64, for c128, left site of the bond, description)
+    "heis": ("heis_f64_L100", "heis_c128_L100", 50, "BASELINE config 3: Heisenberg chain L=100"),
+    "j1j2": ("j1j2_f64_8x6", "j1j2_f64_8x6", 20, "BASELINE config 4: J1-J2 Heisenberg cylinder 8x6 (J2/J1=0.5)"),
+    "hubbard": ("hubbard_f64_L64", "hubbard_f64_L64", 30, "BASELINE config 5: Fermi-Hubbard chain via Jordan-Wigner, d=4, L=64"),
+    "tfim": ("tfim_c128_L100_g0.5", "tfim_c128_L100_g0.5", 50, "BASELINE config 2: transverse-field Ising chain L=100"),
+}
+_MODEL = "heis"
+
+
 def make_inputs(chi, dtype, device, rows=None, row0=0):
     """Seeded synthetic bulk-bond inputs: real MPO site tensors of the model, random L/R/theta.
     Generated per row so that any row shard sees exactly the rows of the global problem."""
-    key = "heis_f64_L100" if dtype == torch.float64 else "heis_c128_L100"
-    mpo = load_mpo(key, dtype)
-    M1, M2 = mpo[50].to(device), mpo[51].to(device)
+    kf, kc, site, _ = MODELS[_MODEL]
+    mpo = load_mpo(kf if dtype == torch.float64 else kc, dtype)
+    M1, M2 = mpo[site].to(device), mpo[site + 1].to(device)
     W = M1.shape[0]
     g = torch.Generator(device="cpu").manual_seed(0)
     rows = chi if rows is None else rows
@@ -186,11 +197,14 @@ def run_reference(args):
 
 
 def workload_config(args, world):
-    return {"workload": f"BASELINE config 3: Heisenberg chain L=100, chi={args.chi}, bulk bond 50|51, W=5, d=2, "
-                        f"{'float64 (real Sp/Sm/Sz MPO)' if args.dtype == 'f64' else 'complex128 (stock Sx/Sy/Sz MPO)'}; "
-                        "one H_eff matvec per step",
-            "chi": args.chi, "d": 2, "W": 5, "L": 100,
-            "parallelism": "single GPU" if world == 1 else f"left-bond row shards x{world} + theta all-gather",
+    kf, kc, site, desc = MODELS[args.model]
+    mpo = load_mpo(kf if args.dtype == "f64" else kc, torch.float64 if args.dtype == "f64" else torch.complex128)
+    M1, M2 = mpo[site], mpo[site + 1]
+    return {"workload": f"{desc}, chi={args.chi}, bulk bond {site}|{site + 1}, MPO bonds "
+                        f"{M1.shape[0]}-{M1.shape[1]}-{M2.shape[1]}, d={M1.shape[2]}, "
+                        f"{'float64' if args.dtype == 'f64' else 'complex128'}; one H_eff matvec per step",
+            "chi": args.chi, "d": int(M1.shape[2]), "W": int(M1.shape[0]), "model": args.model,
+            "parallelism": "single GPU" if world == 1 else f"left-bond row shards x{world}",
             "l2_policy": "inputs + intermediates per step (>1 GB at chi=2048) exceed the 126 MB L2; no flush needed"}
 
 
@@ -517,7 +531,9 @@ def extras(args, qsb, _lib, dev, dtype, L, M1, M2, R, theta, peak_tf):
 
 
 def main():
+    global _MODEL
     args = parse()
+    _MODEL = args.model
     if args.impl == "reference":
         run_reference(args)
     else:
