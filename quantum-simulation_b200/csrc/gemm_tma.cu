@@ -59,7 +59,9 @@ __device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) __trap();     // ~2 s: a lost TMA completion must fail loudly, not hang
+        // a lost completion must fail loudly, not hang -- but the producer of an arrival-gated matvec may itself be
+        // waiting for a peer GPU, so the limit is generous (~60 s)
+        if (clock64() - t0 > 120000000000LL) __trap();
     }
 }
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
@@ -237,7 +239,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 const long long t0 = clock64();
                 do {
                     asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(g.kflags + kc) : "memory");
-                    if (v < g.kepoch && clock64() - t0 > 20000000000LL) __trap();
+                    if (v < g.kepoch && clock64() - t0 > 100000000000LL) __trap();     // ~50 s: peer never pushed
                 } while (v < g.kepoch);
                 asm volatile("fence.proxy.async.global;" ::: "memory");   // peer-written data -> TMA (async proxy) reads
                 p_chunk_ok = kc;
@@ -366,7 +368,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     const long long t0 = clock64();
                     do {
                         asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(sk.flags + cc) : "memory");
-                        if (v != sk.epoch && clock64() - t0 > 20000000000LL) __trap();
+                        if (v != sk.epoch && clock64() - t0 > 100000000000LL) __trap();
                     } while (v != sk.epoch);
                 }
                 __syncthreads();
