@@ -83,6 +83,9 @@ typedef struct {
        block c only once chunk_flags[c] >= chunk_epoch, so the transfer overlaps the first tiles. */
     int n_chunks, chunk_rot, chunk_epoch;
     const int* chunk_flags;
+    int chunk_local;        /* 1: block chunk_rot is already in place (stream-ordered before this call), do not gate it.
+                               Required when that block is copied on the SAME device: such a copy may need SMs, which the
+                               persistent GEMM would be holding while it waits for the flag. */
 } qsb_heff_desc;
 
 int qsb_heff_workspace_bytes(const qsb_heff_desc* d, size_t* bytes);

@@ -49,6 +49,7 @@ class HeffDesc(C.Structure):
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
         ("n_chunks", C.c_int), ("chunk_rot", C.c_int), ("chunk_epoch", C.c_int),
         ("chunk_flags", C.c_void_p),
+        ("chunk_local", C.c_int),
     ]
 
 
@@ -239,7 +240,7 @@ def _impl_heff_apply(psi, L, M1, M2, R, out, gate=None) -> None:
     dev = _require_cuda(psi, L, M1, M2, R, out)
     d = heff_desc(psi, L, M1, M2, R, out)
     if gate is not None:                   # (flags tensor, n_chunks, rot, epoch): fused all-gather -> matvec
-        flags, d.n_chunks, d.chunk_rot, d.chunk_epoch = gate
+        flags, d.n_chunks, d.chunk_rot, d.chunk_epoch, d.chunk_local = gate
         d.chunk_flags = flags.data_ptr()
     nb = C.c_size_t(0)
     check(lib.qsb_heff_workspace_bytes(C.byref(d), C.byref(nb)), "ApplyMPO")
@@ -250,8 +251,8 @@ def _impl_heff_apply(psi, L, M1, M2, R, out, gate=None) -> None:
         check(lib.qsb_heff_apply(C.byref(d), _stream()), "ApplyMPO")
 
 
-def _impl_heff_apply_gated(psi, L, M1, M2, R, out, flags, n_chunks: int, rot: int, epoch: int) -> None:
-    _impl_heff_apply(psi, L, M1, M2, R, out, gate=(flags, n_chunks, rot, epoch))
+def _impl_heff_apply_gated(psi, L, M1, M2, R, out, flags, n_chunks: int, rot: int, epoch: int, local: int) -> None:
+    _impl_heff_apply(psi, L, M1, M2, R, out, gate=(flags, n_chunks, rot, epoch, local))
 
 
 def _impl_push_shard(src, dst_ptrs: Sequence[int], flag_ptrs: Sequence[int], epoch: int, ticket) -> None:
@@ -460,7 +461,7 @@ def register_ops() -> None:
     tl = torch.library.Library("qsb200", "DEF")
     tl.define("heff_apply(Tensor psi, Tensor L, Tensor M1, Tensor M2, Tensor R, Tensor(a!) out) -> ()")
     tl.define("heff_apply_gated(Tensor psi, Tensor L, Tensor M1, Tensor M2, Tensor R, Tensor(a!) out, Tensor flags, "
-              "int n_chunks, int rot, int epoch) -> ()")
+              "int n_chunks, int rot, int epoch, int local) -> ()")
     tl.define("push_shard(Tensor src, int[] dst_ptrs, int[] flag_ptrs, int epoch, Tensor(a!) ticket) -> ()")
     tl.define("env_left(Tensor env, Tensor M, Tensor site, Tensor(a!) out) -> ()")
     tl.define("env_right(Tensor env, Tensor M, Tensor site, Tensor(a!) out) -> ()")

@@ -34,7 +34,7 @@ struct GemmArgs {
     void*       C; long long c_ms, c_ns, c_zs;
     int force_path;                 // 0 auto, 1 TMA, 2 cp.async
     // optional k-chunk gating (TMA path only): see TArgs in gemm_tma.cu
-    int ksplit = 1, krot = 0, kepoch = 0;
+    int ksplit = 1, krot = 0, kepoch = 0, klocal = 0;
     const int* kflags = nullptr;
 };
 int gemm_launch(const GemmArgs& g, cudaStream_t stream);

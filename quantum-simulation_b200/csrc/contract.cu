@@ -384,6 +384,7 @@ extern "C" int qsb_heff_apply(const qsb_heff_desc* d, void* stream_) {
     if (d->n_chunks > 1) {           // fused all-gather -> GEMM: gate the k chunks on their arrival flags
         if (!d->chunk_flags) return QSB_ERR_ARG;
         g1.ksplit = d->n_chunks; g1.krot = d->chunk_rot; g1.kepoch = d->chunk_epoch; g1.kflags = d->chunk_flags;
+        g1.klocal = d->chunk_local;
         g1.force_path = 1;
     }
     if ((rc = gemm_launch(g1, stream))) return rc;

@@ -42,7 +42,7 @@ struct TArgs {
     double sgnA, sgnB;
     // k-chunk gating (fused all-gather -> GEMM): the k range is ksplit equal chunks, chunk c becomes readable when
     // kflags[c] >= kepoch (set by the peer that pushed it); chunks are visited starting from chunk krot
-    int ksplit, krot, kepoch;
+    int ksplit, krot, kepoch, klocal;    // klocal: chunk krot is already in place, never wait for it
     const int* kflags;
 };
 
@@ -218,7 +218,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     Sched ps; ps.init(sk.U_sk, sk.ipt, sk.T_sk, sk.dp_waves, G, cta, g.ksplit > 1);
     int p_tile = -1, p_it = 0, p_it1 = 0, p_m0 = 0, p_n0 = 0, p_z = 0;
     int pj = 0;                              // CTA-local index of the next k-iteration to issue
-    int p_chunk_ok = -1;                     // last gated k chunk known to have arrived
+    int p_chunk_ok = (g.ksplit > 1 && g.klocal) ? g.krot : -1;     // last gated k chunk known to have arrived
     bool p_more = true;
     auto produce = [&]() {                   // issue one k-iteration (if any is left); thread 0 only
         if (p_it == p_it1) {
@@ -580,11 +580,11 @@ int gemm_tma_try(const GemmArgs& g, cudaStream_t stream, bool* used) {
     t.b_has_p = (b.has_p && g.P > 1); t.b_has_z = (b.has_z && g.Z > 1);
     t.C = (char*)g.C; t.c_ms = g.c_ms; t.c_ns = g.c_ns; t.c_zs = g.Z > 1 ? g.c_zs : 0;
     t.sgnA = g.conjA ? -1.0 : 1.0; t.sgnB = g.conjB ? -1.0 : 1.0;
-    t.ksplit = 1; t.krot = 0; t.kepoch = 0; t.kflags = nullptr;
+    t.ksplit = 1; t.krot = 0; t.kepoch = 0; t.klocal = 0; t.kflags = nullptr;
     if (g.ksplit > 1) {
         const int ktiles = (g.K + BK - 1) / BK;
         if (g.P != 1 || g.K % BK != 0 || ktiles % g.ksplit != 0 || !g.kflags) return QSB_ERR_STRIDE;
-        t.ksplit = g.ksplit; t.krot = g.krot % g.ksplit; t.kepoch = g.kepoch; t.kflags = g.kflags;
+        t.ksplit = g.ksplit; t.krot = g.krot % g.ksplit; t.kepoch = g.kepoch; t.kflags = g.kflags; t.klocal = g.klocal;
     }
     int rc;
     if (cplx) {

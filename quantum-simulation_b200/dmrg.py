@@ -197,7 +197,7 @@ class ApplyMPO(_BaseContractModule):
                 ob = out_dev[b * rows * per_out:(b + 1) * rows * per_out]
                 if n_chunks > 1:
                     try:
-                        _lib.ops.heff_apply_gated(theta_dev, Lb, M1, M2, R, ob, pipe["flags"], n_chunks, 0, epoch)
+                        _lib.ops.heff_apply_gated(theta_dev, Lb, M1, M2, R, ob, pipe["flags"], n_chunks, 0, epoch, 0)
                     except ValueError:                     # operands the TMA-staged (gated) GEMM cannot describe
                         main.wait_stream(pipe["h2d"])
                         n_chunks = 1

@@ -201,15 +201,20 @@ class FusedShardedApplyMPO:
         if self.push == "sm":
             self._ops.push_shard(v, self.dst_ptrs[b], self.flag_ptrs, self.epoch, self.ticket)
             self._ops.heff_apply_gated(self.bufs[b], L_rows, M1, M2, R, out, self.flags, self.world, self.rank,
-                                       self.epoch)
+                                       self.epoch, 0)
             return out
         # copy engines on a side stream: the pushes run WHILE the gated GEMM already works on the local block
         main = torch.cuda.current_stream(v.device)
+        # own block: a plain stream-ordered copy on the main stream (a same-device copy may run on SMs, which the
+        # persistent GEMM would be holding while it waited for the flag -> never gate the local block on a flag)
+        nloc = v.numel()
+        self.bufs[b][self.rank * nloc:(self.rank + 1) * nloc].copy_(v)
         ready = torch.cuda.Event()
         ready.record(main)
         dones = []
-        for si, side in enumerate(self._side):       # two copy streams: destinations dealt alternately
-            targets = self._order[si::len(self._side)]
+        peers = self._order[1:]
+        for si, side in enumerate(self._side):       # two copy streams: peer destinations dealt alternately
+            targets = peers[si::len(self._side)]
             if not targets:
                 continue
             side.wait_event(ready)
@@ -219,7 +224,7 @@ class FusedShardedApplyMPO:
                 done = torch.cuda.Event()
                 done.record(side)
                 dones.append(done)
-        self._ops.heff_apply_gated(self.bufs[b], L_rows, M1, M2, R, out, self.flags, self.world, self.rank, self.epoch)
+        self._ops.heff_apply_gated(self.bufs[b], L_rows, M1, M2, R, out, self.flags, self.world, self.rank, self.epoch, 1)
         for done in dones:
             main.wait_event(done)        # v_shard may be reused once our outgoing copies have left
         return out
