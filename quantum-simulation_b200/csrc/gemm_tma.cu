@@ -218,7 +218,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     Sched ps; ps.init(sk.U_sk, sk.ipt, sk.T_sk, sk.dp_waves, G, cta, g.ksplit > 1);
     int p_tile = -1, p_it = 0, p_it1 = 0, p_m0 = 0, p_n0 = 0, p_z = 0;
     int pj = 0;                              // CTA-local index of the next k-iteration to issue
-    int p_chunk_ok = (g.ksplit > 1 && g.klocal) ? g.krot : -1;     // last gated k chunk known to have arrived
+    int p_chunk_ok = -1;                     // last gated k chunk known to have arrived
     bool p_more = true;
     auto produce = [&]() {                   // issue one k-iteration (if any is left); thread 0 only
         if (p_it == p_it1) {
@@ -234,7 +234,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             const int per = ktiles / g.ksplit;
             const int c = p_it / per;
             int kc = c + g.krot; if (kc >= g.ksplit) kc -= g.ksplit;
-            if (kc != p_chunk_ok) {
+            if (kc != p_chunk_ok && !(g.klocal && kc == g.krot)) {     // the local block is never gated
                 int v;
                 const long long t0 = clock64();
                 do {
