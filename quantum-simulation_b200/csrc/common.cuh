@@ -51,17 +51,6 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
         : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-__device__ __forceinline__ double lds64(uint32_t addr) {
-    double v;
-    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ double2 lds128(uint32_t addr) {
-    double2 v;
-    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
-    return v;
-}
-
 template <int BYTES>
 __device__ __forceinline__ void cp_async(uint32_t dst, const void* src, bool ok) {
     int sz = ok ? BYTES : 0;     // src-size 0 => destination zero-filled, nothing read
@@ -91,17 +80,6 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" :: "r"(bar), "r"(parity) : "memory");
 }
 // tiled TMA loads, global -> shared, completion on an mbarrier
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
