@@ -11,9 +11,10 @@ from . import _lib
 from ._lib import launch_counters, load as load_library
 from .mps import MPS, random_mps
 from .eigensolver import lanczos_ground_state, clear_workspaces
+from .observables import mpo_expectation, energy_expectation, energy_variance
 from .dmrg import (ApplyMPO, LeftEnvUpdate, RightEnvUpdate, EnvironmentManager, Sweeps, DMRG,
                    set_contract_backend)
 
 __all__ = ["MPS", "random_mps", "lanczos_ground_state", "clear_workspaces", "ApplyMPO", "LeftEnvUpdate",
            "RightEnvUpdate", "EnvironmentManager", "Sweeps", "DMRG", "set_contract_backend", "launch_counters",
-           "load_library"]
+           "load_library", "mpo_expectation", "energy_expectation", "energy_variance"]

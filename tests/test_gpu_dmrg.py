@@ -135,3 +135,62 @@ def test_baseline_config2_first_sweep_against_reference():
     # the reference-vs-restatement spread over updates >= 20 is 4e-7; allow the same order of magnitude
     assert rel[20:].max() < 5e-6, f"deviation {rel[20:].max():.2e} (reference-vs-restatement spread {ref_spread[20:].max():.2e})"
     assert abs(E[-1] - Eg[-1]) / abs(Eg[-1]) < 1e-6
+
+
+# ----------------------------------------------------------------------------- environment-based observables (f.4)
+def _dense_mpo(mpo):
+    """Dense matrix of an open-boundary MPO (small systems): the checker for the environment contractions."""
+    acc = mpo[0][0]                                     # (Wr, d, d) after fixing the left boundary index
+    for M in mpo[1:]:
+        acc = torch.einsum("wab,wvcd->vacbd", acc, M)
+        v, a, c, b, d = acc.shape
+        acc = acc.reshape(v, a * c, b * d)
+    return acc[0]
+
+
+@pytest.mark.parametrize("name", ["nb02_tfim_L6", "nb03_heis_L4"])
+def test_energy_variance_by_environments(name):
+    """<H> and Var(H) from left-environment contractions against the dense d^N computation the reference uses
+    (dmrg_observables.py:539-582), on converged notebook runs (dmrg_04 stores Var(H) = 1.35e-12 for TFIM L=6)."""
+    z, E, dm, mps = run_case(name)
+    dt = mps.B[0].dtype
+    mpo = golden_mpo(str(z[f"{name}/mpo"]), dt, DEV)
+    state = mps.B[0].detach()
+    for t in list(mps.B)[1:]:
+        state = torch.tensordot(state, t.detach(), dims=([-1], [0]))
+    psi = state.reshape(-1)
+    H = _dense_mpo(mpo)
+    Hpsi = H @ psi
+    nrm = torch.vdot(psi, psi).real
+    e_dense = (torch.vdot(psi, Hpsi).real / nrm).item()
+    var_dense = (torch.vdot(Hpsi, Hpsi).real / nrm).item() - e_dense ** 2
+    e_env = float(qsb.energy_expectation(mps, mpo))
+    var_env = float(qsb.energy_variance(mps, mpo))
+    assert abs(e_env - e_dense) <= 1e-12 * max(1.0, abs(e_dense))
+    assert abs(e_env - E[-1]) <= 1e-9                      # the last Ritz value is the energy of the final state
+    assert abs(var_env - max(var_dense, 0.0)) <= 1e-11
+    assert 0.0 <= var_env < 1e-9
+    with pytest.raises(ValueError):
+        qsb.energy_variance(mps, mpo, form="C")
+    with pytest.raises(ValueError):
+        qsb.energy_variance(mps, mpo[:-1])
+
+
+def test_energy_variance_unconverged_state_matches_dense():
+    """A random (unconverged) MPS has a large variance: checks <H^2> through the W^2-bond squared MPO."""
+    dt = torch.complex128
+    mps = quiet(qsb.MPS, 8, 2, 12, "cpu", dt, 21).to(DEV)
+    mpo = golden_mpo("heis_c128_L20", dt, DEV)
+    mpo8 = [mpo[0], mpo[1]] + [mpo[5]] * 4 + [mpo[-2], mpo[-1]]
+    state = mps.B[0].detach()
+    for t in list(mps.B)[1:]:
+        state = torch.tensordot(state, t.detach(), dims=([-1], [0]))
+    psi = state.reshape(-1)
+    H = _dense_mpo(mpo8)
+    Hpsi = H @ psi
+    nrm = torch.vdot(psi, psi).real
+    e_dense = (torch.vdot(psi, Hpsi).real / nrm).item()
+    var_dense = (torch.vdot(Hpsi, Hpsi).real / nrm).item() - e_dense ** 2
+    assert abs(float(qsb.energy_expectation(mps, mpo8)) - e_dense) <= 1e-12 * max(1.0, abs(e_dense))
+    assert abs(float(qsb.energy_variance(mps, mpo8)) - var_dense) <= 1e-11 * max(1.0, var_dense)
+    assert var_dense > 1e-3
