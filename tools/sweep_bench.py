@@ -83,7 +83,14 @@ def case_c2():
         qsvd.FAST_MIN = 256
         return out
     Eg, tg, dm = run_gpu(key, 100, 512, dt, 10)
+    t0 = time.perf_counter()
+    mp = [m.to(DEV) for m in mpo(key, dt)]
+    e_env = float(qsb.energy_expectation(dm.mps, mp))
+    var_env = float(qsb.energy_variance(dm.mps, mp))
+    torch.cuda.synchronize()
+    t_obs = time.perf_counter() - t0
     res = {"case": "C2 TFIM L=100 g=0.5 chi=512, 10 sweeps", "mpo": key, "gpu_s": tg, "gpu_s_per_sweep": tg / 10,
+           "energy_by_environments": e_env, "variance_by_environments": var_env, "observables_s": t_obs,
            "E_final_gpu": float(Eg[-1]), "bond_dim_mid": dm.history["bond_dims"][-50],
            "E_end_of_sweep": [float(Eg[(k + 1) * 198 - 1]) for k in range(10)]}
     if "--cpu" in sys.argv:
