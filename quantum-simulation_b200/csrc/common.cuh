@@ -98,14 +98,15 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
 // fastest inside a group, so that one wave of 148 CTAs covers a ~12 x 12 patch: the A and B panels a wave streams
 // from HBM are ~2 * sqrt(148) instead of tiles_m + 148 / tiles_m (L2-friendly rasterisation).
 constexpr int kRasterGroup = 12;
-__device__ __forceinline__ void tile_coords(int bid, int tiles_m, int tiles_n, int& tm, int& tn, int& z) {
+__device__ __forceinline__ void tile_coords(int bid, int tiles_m, int tiles_n, int& tm, int& tn, int& z,
+                                            int group = kRasterGroup) {
     const int per_z = tiles_m * tiles_n;
     z = bid / per_z;
     const int r = bid - z * per_z;
-    const int per_group = kRasterGroup * tiles_n;
+    const int per_group = group * tiles_n;
     const int grp = r / per_group;
-    const int first = grp * kRasterGroup;
-    const int gsz = min(kRasterGroup, tiles_m - first);
+    const int first = grp * group;
+    const int gsz = min(group, tiles_m - first);
     const int rr = r - grp * per_group;
     tn = rr / gsz;
     tm = first + (rr - tn * gsz);

@@ -16,6 +16,7 @@
 // * Out-of-range k (and rows of KC operands) are zero-filled by the TMA, so ragged extents need no copies.
 #include "common.cuh"
 #include <mutex>
+#include <cstdlib>
 
 namespace qsb {
 
@@ -42,6 +43,7 @@ struct TArgs {
     double sgnA, sgnB;
     // k-chunk gating (fused all-gather -> GEMM): the k range is ksplit equal chunks, chunk c becomes readable when
     // kflags[c] >= kepoch (set by the peer that pushed it); chunks are visited starting from chunk krot
+    int raster;                 // tile rows per rasterisation group
     int ksplit, krot, kepoch, klocal;    // klocal: chunk krot is already in place, never wait for it
     const int* kflags;
 };
@@ -224,7 +226,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         if (p_it == p_it1) {
             if (!p_more || !ps.next(p_tile, p_it, p_it1)) { p_more = false; return; }
             int tm, tn;
-            tile_coords(p_tile, g.tiles_m, g.tiles_n, tm, tn, p_z);
+            tile_coords(p_tile, g.tiles_m, g.tiles_n, tm, tn, p_z, g.raster);
             p_m0 = tm * C::BM; p_n0 = tn * C::BN;
         }
         const int slot = pj % S;
@@ -384,7 +386,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         }
         // store: lane owns rows frag_index<A>(i, g8) and columns frag_index<B>(j, 2*t4), frag_index<B>(j, 2*t4+1)
         int tm, tn, z;
-        tile_coords(tile, g.tiles_m, g.tiles_n, tm, tn, z);
+        tile_coords(tile, g.tiles_m, g.tiles_n, tm, tn, z, g.raster);
         const int m0 = tm * C::BM, n0 = tn * C::BN;
         char* Cz = g.C + g.c_zs * z * C::ES;
         bool vec_ok = false;
@@ -580,6 +582,11 @@ int gemm_tma_try(const GemmArgs& g, cudaStream_t stream, bool* used) {
     t.b_has_p = (b.has_p && g.P > 1); t.b_has_z = (b.has_z && g.Z > 1);
     t.C = (char*)g.C; t.c_ms = g.c_ms; t.c_ns = g.c_ns; t.c_zs = g.Z > 1 ? g.c_zs : 0;
     t.sgnA = g.conjA ? -1.0 : 1.0; t.sgnB = g.conjB ? -1.0 : 1.0;
+    {
+        static int raster_env = -1;          // experiment knob: QSB_RASTER_GROUP overrides the default group size
+        if (raster_env < 0) { const char* e = getenv("QSB_RASTER_GROUP"); raster_env = e ? atoi(e) : 0; }
+        t.raster = raster_env > 0 ? raster_env : kRasterGroup;
+    }
     t.ksplit = 1; t.krot = 0; t.kepoch = 0; t.klocal = 0; t.kflags = nullptr;
     if (g.ksplit > 1) {
         const int ktiles = (g.K + BK - 1) / BK;
