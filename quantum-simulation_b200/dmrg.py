@@ -93,6 +93,16 @@ def _dev_tensor(t: torch.Tensor) -> torch.Tensor:
     return _lib._resolved(t.detach() if t.requires_grad else t)
 
 
+def _same_dtype(where: str, *tensors: torch.Tensor) -> None:
+    """The kernels read every operand with the dtype of the first: mixed dtypes are an error, not a cast."""
+    dt = tensors[0].dtype
+    if dt not in (torch.float64, torch.complex128):
+        raise ValueError(f"[{where}] unsupported dtype {dt}: the contraction kernels take float64 or complex128")
+    for t in tensors[1:]:
+        if t.dtype != dt:
+            raise ValueError(f"[{where}] dtype mismatch: {dt} vs {t.dtype}")
+
+
 class ApplyMPO(_BaseContractModule):
     r"""H_eff . theta = L . M1 . M2 . R . theta for the two-site block (dmrg.py:165-248).
 
@@ -102,6 +112,7 @@ class ApplyMPO(_BaseContractModule):
 
     def forward(self, psi_flat: torch.Tensor, L: torch.Tensor, M1: torch.Tensor, M2: torch.Tensor,
                 R: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        _same_dtype("ApplyMPO", psi_flat, L, M1, M2, R)
         if psi_flat.device.type == "cpu" and L.device.type == "cuda":
             return self._forward_host(psi_flat, L, M1, M2, R, out)
         psi, L, M1, M2, R = (_dev_tensor(t) for t in (psi_flat, L, M1, M2, R))
@@ -218,6 +229,7 @@ class LeftEnvUpdate(_BaseContractModule):
     """L[p+1][w', c'_bra, c_ket] = sum L[p] . conj(A) . M . A  (dmrg.py:251-278); returns contiguous (W', chi', chi')."""
 
     def forward(self, Lp: torch.Tensor, M: torch.Tensor, Ap: torch.Tensor) -> torch.Tensor:
+        _same_dtype("LeftEnvUpdate", Lp, M, Ap)
         Lp, M, Ap = (_dev_tensor(t) for t in (Lp, M, Ap))
         if not M.is_contiguous():
             M = M.contiguous()
@@ -230,6 +242,7 @@ class RightEnvUpdate(_BaseContractModule):
     """R[p][w, a'_bra, a_ket] = sum M . R[p+1] . B . conj(B)  (dmrg.py:281-308); returns contiguous (W, chi, chi)."""
 
     def forward(self, M: torch.Tensor, Rnext: torch.Tensor, Bp1: torch.Tensor) -> torch.Tensor:
+        _same_dtype("RightEnvUpdate", M, Rnext, Bp1)
         M, Rnext, Bp1 = (_dev_tensor(t) for t in (M, Rnext, Bp1))
         if not M.is_contiguous():
             M = M.contiguous()

@@ -151,3 +151,58 @@ def test_mps_position_keeps_state_and_canonical_form():
                 assert torch.linalg.norm(b @ b.conj().T - torch.eye(b.shape[0], dtype=b.dtype)) < 1e-12
     with pytest.raises(ValueError):
         mps.position(7)
+
+
+def test_c_abi_from_plain_c(tmp_path):
+    """Compile and run a plain-C consumer of include/qsb200.h against the built library (gcc, no GPU needed)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    _lib.load()
+    exe = str(tmp_path / "abi_check")
+    cmd = [gcc, "-std=c11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "c", "abi_check.c"), "-L", libdir, "-lqsb200", f"-Wl,-rpath,{libdir}", "-o", exe]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert run.returncode == 0, run.stdout + run.stderr
+    assert "abi_check ok" in run.stdout
+
+
+def test_dtype_mismatch_is_a_value_error():
+    """Mixed dtypes must be rejected before any pointer reaches the kernels (CPU tensors suffice to check)."""
+    L = torch.ones(1, 1, 1, dtype=torch.complex128)
+    M = torch.ones(1, 1, 2, 2, dtype=torch.float64)
+    with pytest.raises(ValueError, match="dtype"):
+        qsb.ApplyMPO()(torch.ones(4, dtype=torch.float64), L, M, M, L.real)
+    with pytest.raises(ValueError, match="dtype"):
+        qsb.LeftEnvUpdate()(L, M, torch.ones(1, 2, 1, dtype=torch.complex128))
+    with pytest.raises(ValueError, match="dtype"):
+        qsb.RightEnvUpdate()(M, L, torch.ones(1, 2, 1, dtype=torch.complex128))
+    with pytest.raises(ValueError, match="dtype"):
+        qsb.ApplyMPO()(torch.ones(4, dtype=torch.float32), L.real.float(), M.float(), M.float(), L.real.float())
+
+
+def test_mps_constructor_and_position_match_reference_fixture():
+    """tests/golden/mps.npz holds the unmodified reference's MPS tensors after construction and after a sequence of
+    position() moves; the mirror reproduces them bit for bit on the CPU (same torch ops in the same order)."""
+    import io
+    import contextlib
+    import numpy as np
+    z = np.load(os.path.join(ROOT, "tests", "golden", "mps.npz"))
+    for tag, dt in (("c128", torch.complex128), ("f64", torch.float64)):
+        N, d, chi, seed = (int(x) for x in z[f"{tag}/cfg"])
+        with contextlib.redirect_stdout(io.StringIO()):
+            m = qsb.MPS(N, d, chi, "cpu", dt, seed=seed)
+            for p in range(N):
+                assert np.array_equal(m.B[p].detach().numpy(), z[f"{tag}/init_B{p}"])
+            for tgt in z[f"{tag}/moves"]:
+                m.position(int(tgt))
+        for p in range(N):
+            assert np.allclose(m.A[p].detach().numpy(), z[f"{tag}/A{p}"], rtol=0, atol=1e-15)
+            assert np.allclose(m.B[p].detach().numpy(), z[f"{tag}/B{p}"], rtol=0, atol=1e-15)
+        for p in range(N + 1):
+            assert np.allclose(m.sWeight[p].detach().numpy(), z[f"{tag}/s{p}"], rtol=0, atol=1e-15)
