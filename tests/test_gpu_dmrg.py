@@ -194,3 +194,24 @@ def test_energy_variance_unconverged_state_matches_dense():
     assert abs(float(qsb.energy_expectation(mps, mpo8)) - e_dense) <= 1e-12 * max(1.0, abs(e_dense))
     assert abs(float(qsb.energy_variance(mps, mpo8)) - var_dense) <= 1e-11 * max(1.0, var_dense)
     assert var_dense > 1e-3
+
+
+def test_mps_built_on_the_gpu_is_right_canonical_and_drives_dmrg():
+    """'Next' row f.3: the MPS mirror canonicalises directly on the GPU (torch QR on device) -- no CPU round trip at
+    large chi -- and the result is a valid start state for DMRG (energy decreases monotonically sweep to sweep)."""
+    dt = torch.float64
+    mps = quiet(qsb.MPS, 20, 2, 32, DEV, dt, 4)
+    assert mps.B[0].device.type == "cuda" and mps.ortho_center == 0
+    for p in range(1, 20):
+        b = mps.B[p].reshape(mps.B[p].shape[0], -1)
+        assert float(torch.linalg.norm(b @ b.T - torch.eye(b.shape[0], dtype=dt, device=DEV))) < 1e-12
+    assert abs(float(torch.linalg.norm(mps.B[0])) - 1.0) < 1e-13
+    mpo = golden_mpo("heis_f64_L20", dt, DEV)
+    sw = qsb.Sweeps(3)
+    sw.set_schedule(maxdim=[32] * 3, cutoff=[0.0] * 3)
+    dm = quiet(qsb.DMRG, mps, mpo, device=DEV, dtype=dt)
+    E, _ = quiet(dm, sw, dispon=0)
+    ends = [E[(k + 1) * 38 - 1] for k in range(3)]
+    assert ends[0] >= ends[1] - 1e-12 >= ends[2] - 2e-12
+    assert abs(ends[2] - (-8.682473319650)) < 1e-6          # SURVEY section 4 calibration value (chi = 32)
+    assert abs(float(qsb.energy_expectation(dm.mps, mpo)) - ends[2]) < 1e-9
