@@ -76,6 +76,16 @@ def _check_mpo_shapes(Ms: List[torch.Tensor], ML: torch.Tensor, MR: torch.Tensor
     assert MR.shape[0] == Ms[-1].shape[1], f"MR W={MR.shape[0]} must match Ms[-1].Wr={Ms[-1].shape[1]}"
 
 
+def _matmul2d(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """(m x k) @ (k x n) on the library's FP64 tensor-core GEMM core (theta build, dmrg.py:645-646 / 659-660);
+    operands with no unit stride are made contiguous first (they are chi^2 d elements)."""
+    if a.stride(0) != 1 and a.stride(1) != 1:
+        a = a.contiguous()
+    if b.stride(0) != 1 and b.stride(1) != 1:
+        b = b.contiguous()
+    return _lib.gemm(_dev_tensor(a), _dev_tensor(b))
+
+
 class _BaseContractModule(nn.Module):
     """dmrg.py:127-162: validates and stores the backend policy."""
 
@@ -360,8 +370,8 @@ class DMRG(nn.Module):
                     sw = torch.diagonal(sw, 0)
                 l, s, m = left_t.shape
                 _m, t, r = right_t.shape
-                psi = torch.matmul(torch.mul(left_t, sw.to(left_t.dtype).view(-1, 1, 1)).reshape(l * s, m),
-                                   right_t.reshape(m, t * r))
+                psi = _matmul2d(torch.mul(left_t, sw.to(left_t.dtype).view(-1, 1, 1)).reshape(l * s, m),
+                                right_t.reshape(m, t * r))
             else:
                 left_t, right_t = A[p], A[p + 1]
                 sw = sWeight[p + 2]
@@ -369,8 +379,8 @@ class DMRG(nn.Module):
                     sw = torch.diagonal(sw, 0)
                 l, s, m = left_t.shape
                 _m, t, r = right_t.shape
-                psi = torch.matmul(left_t.reshape(l * s, m),
-                                   torch.mul(right_t, sw.to(right_t.dtype).view(1, 1, -1)).reshape(m, t * r))
+                psi = _matmul2d(left_t.reshape(l * s, m),
+                                torch.mul(right_t, sw.to(right_t.dtype).view(1, 1, -1)).reshape(m, t * r))
             chil, chir = l, r
             psi_flat = psi.reshape(-1)
 
