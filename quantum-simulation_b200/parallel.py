@@ -263,6 +263,10 @@ class CudaEngine:
         self._left, self._right = LeftEnvUpdate(), RightEnvUpdate()
         self.vector_ops = None                       # None -> CudaVectorOps
 
+    def matmul(self, a, b):
+        from .dmrg import _matmul2d
+        return _matmul2d(a, b)
+
     def env_left(self, Lp, M, A):
         return self._left(Lp, M, A)
 
@@ -492,14 +496,14 @@ class ShardedDMRG:
                     sw = torch.diagonal(sw, 0)
                 l, s, m = lt.shape
                 _m, t, r = rt.shape
-                psi = torch.matmul(torch.mul(lt, sw.to(lt.dtype).view(-1, 1, 1)).reshape(l * s, m), rt.reshape(m, t * r))
+                psi = self.engine.matmul(torch.mul(lt, sw.to(lt.dtype).view(-1, 1, 1)).reshape(l * s, m), rt.reshape(m, t * r))
             else:                                                     # (dmrg.py:647-660)
                 lt, rt, sw = A[p], A[p + 1], sW[p + 2]
                 if sw.dim() == 2:
                     sw = torch.diagonal(sw, 0)
                 l, s, m = lt.shape
                 _m, t, r = rt.shape
-                psi = torch.matmul(lt.reshape(l * s, m), torch.mul(rt, sw.to(rt.dtype).view(1, 1, -1)).reshape(m, t * r))
+                psi = self.engine.matmul(lt.reshape(l * s, m), torch.mul(rt, sw.to(rt.dtype).view(1, 1, -1)).reshape(m, t * r))
             chil, chir = l, r
             self._tick("theta")
             R_full = self._full(R[p + 2])

@@ -15,6 +15,10 @@ class CpuEngine:
         return orc.apply_mpo(v, L, M1, M2, R, out=out)
 
     @staticmethod
+    def matmul(a, b):
+        return torch.matmul(a, b)
+
+    @staticmethod
     def env_left(Lp, M, A):
         return orc.left_env_update(Lp, M, A).contiguous()
 
