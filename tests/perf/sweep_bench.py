@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Sweep-level measurements (BASELINE.json: "DMRG sweep time"): full DMRG runs through the drop-in DMRG class on
 the GPU, energy parity against the CPU oracle where it finishes in seconds, and a per-bond-step breakdown at
-chi = 2048.  Prints one JSON object per case.  Usage: python tools/sweep_bench.py [c1] [c2] [c3] [svd]"""
+chi = 2048.  Prints one JSON object per case.  Usage: python tests/perf/sweep_bench.py [c1] [c2] [c3] [svd]"""
 import contextlib
 import io
 import json
@@ -12,7 +12,7 @@ import time
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import quantum_simulation_b200 as qsb          # noqa: E402
 from oracle import dmrg_oracle as orc          # noqa: E402
