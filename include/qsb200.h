@@ -83,6 +83,10 @@ typedef struct {
        block c only once chunk_flags[c] >= chunk_epoch, so the transfer overlaps the first tiles. */
     int n_chunks, chunk_rot, chunk_epoch;
     const int* chunk_flags;
+    int chunk_axis;         /* 0: the blocks are ROW blocks of theta (the k range of step 1; multi-GPU exchange).
+                               1: the blocks are COLUMN blocks of theta viewed as (chi_l_in, d1*d2*chi_r): an output tile
+                                  of step 1 then depends on ONE block only, so tiles start as soon as their block has
+                                  landed (host upload with qsb_upload_columns); chunk_rot / chunk_local are ignored. */
     int chunk_local;        /* 1: block chunk_rot is already in place (stream-ordered before this call), do not gate it.
                                Required when that block is copied on the SAME device: such a copy may need SMs, which the
                                persistent GEMM would be holding while it waits for the flag. */
@@ -109,6 +113,11 @@ int qsb_push_shard(const void* src, size_t bytes, void* const* dst, int* const* 
    memory (cudaMemcpyDefault): the same gating then overlaps a host->device upload of theta with the step-1 GEMM. */
 int qsb_push_shard_dma(const void* src, size_t bytes, void* const* dst, int* const* flag, int count, int epoch,
                        void* stream);
+
+/* Upload a row-major (rows x row_elems) matrix from PINNED HOST memory in n_chunks column blocks on the copy engines
+   (cudaMemcpy2DAsync), each followed by a stream-ordered flag write flags[c] = epoch; pairs with chunk_axis = 1. */
+int qsb_upload_columns(const void* src_host, void* dst, int64_t rows, int64_t row_elems, int elem_bytes, int n_chunks,
+                       int* flags, int epoch, void* stream);
 
 /* ---- environment updates (dmrg.py:254-308) ----------------------------- */
 typedef struct {

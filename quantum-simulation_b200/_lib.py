@@ -31,7 +31,7 @@ EXPORTS = [
     "qsb_heff_workspace_bytes", "qsb_heff_apply", "qsb_heff_flops", "qsb_heff_set_stage_events",
     "qsb_env_workspace_bytes", "qsb_env_left", "qsb_env_right", "qsb_env_flops",
     "qsb_lz_scratch_bytes", "qsb_lz_dot", "qsb_lz_axpy_norm", "qsb_lz_scale", "qsb_lz_combine",
-    "qsb_strided_copy3", "qsb_gemm", "qsb_probe_dmma", "qsb_push_shard", "qsb_push_shard_dma",
+    "qsb_strided_copy3", "qsb_gemm", "qsb_probe_dmma", "qsb_push_shard", "qsb_push_shard_dma", "qsb_upload_columns",
 ]
 
 
@@ -49,6 +49,7 @@ class HeffDesc(C.Structure):
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
         ("n_chunks", C.c_int), ("chunk_rot", C.c_int), ("chunk_epoch", C.c_int),
         ("chunk_flags", C.c_void_p),
+        ("chunk_axis", C.c_int),
         ("chunk_local", C.c_int),
     ]
 
@@ -119,6 +120,7 @@ def load() -> C.CDLL:
     lib.qsb_strided_copy3.argtypes = [i32, C.POINTER(i64), vp, C.POINTER(i64), vp, i32, vp]
     lib.qsb_gemm.argtypes = [C.POINTER(GemmDesc), vp]
     lib.qsb_push_shard.argtypes = [vp, C.c_size_t, C.POINTER(vp), C.POINTER(vp), i32, i32, vp, vp]
+    lib.qsb_upload_columns.argtypes = [vp, vp, i64, i64, i32, i32, vp, i32, vp]
     lib.qsb_push_shard_dma.argtypes = [vp, C.c_size_t, C.POINTER(vp), C.POINTER(vp), i32, i32, vp]
     lib.qsb_probe_dmma.argtypes = [i32, C.POINTER(C.c_double), vp, vp]
     for name in EXPORTS:          # every symbol include/qsb200.h declares must be exported
@@ -240,7 +242,8 @@ def _impl_heff_apply(psi, L, M1, M2, R, out, gate=None) -> None:
     dev = _require_cuda(psi, L, M1, M2, R, out)
     d = heff_desc(psi, L, M1, M2, R, out)
     if gate is not None:                   # (flags tensor, n_chunks, rot, epoch): fused all-gather -> matvec
-        flags, d.n_chunks, d.chunk_rot, d.chunk_epoch, d.chunk_local = gate
+        flags, d.n_chunks, d.chunk_rot, d.chunk_epoch, d.chunk_local = gate[:5]
+        d.chunk_axis = gate[5] if len(gate) > 5 else 0
         d.chunk_flags = flags.data_ptr()
     nb = C.c_size_t(0)
     check(lib.qsb_heff_workspace_bytes(C.byref(d), C.byref(nb)), "ApplyMPO")
@@ -253,6 +256,21 @@ def _impl_heff_apply(psi, L, M1, M2, R, out, gate=None) -> None:
 
 def _impl_heff_apply_gated(psi, L, M1, M2, R, out, flags, n_chunks: int, rot: int, epoch: int, local: int) -> None:
     _impl_heff_apply(psi, L, M1, M2, R, out, gate=(flags, n_chunks, rot, epoch, local))
+
+
+def _impl_heff_apply_colgated(psi, L, M1, M2, R, out, flags, n_chunks: int, epoch: int) -> None:
+    _impl_heff_apply(psi, L, M1, M2, R, out, gate=(flags, n_chunks, 0, epoch, 0, 1))
+
+
+def upload_columns(src_host: torch.Tensor, dst: torch.Tensor, rows: int, row_elems: int, n_chunks: int,
+                   flags: torch.Tensor, epoch: int) -> None:
+    """Pinned host (rows x row_elems) matrix -> device in column blocks + per-block flags, on the CURRENT stream."""
+    if src_host.device.type != "cpu" or not src_host.is_pinned():
+        raise ValueError("upload_columns: the source must be pinned host memory")
+    dev = _require_cuda(dst, flags)
+    with torch.cuda.device(dev):
+        check(load().qsb_upload_columns(src_host.data_ptr(), dst.data_ptr(), rows, row_elems, src_host.element_size(),
+                                        n_chunks, flags.data_ptr(), epoch, _stream()), "upload_columns")
 
 
 def _impl_push_shard(src, dst_ptrs: Sequence[int], flag_ptrs: Sequence[int], epoch: int, ticket) -> None:
@@ -462,6 +480,8 @@ def register_ops() -> None:
     tl.define("heff_apply(Tensor psi, Tensor L, Tensor M1, Tensor M2, Tensor R, Tensor(a!) out) -> ()")
     tl.define("heff_apply_gated(Tensor psi, Tensor L, Tensor M1, Tensor M2, Tensor R, Tensor(a!) out, Tensor flags, "
               "int n_chunks, int rot, int epoch, int local) -> ()")
+    tl.define("heff_apply_colgated(Tensor psi, Tensor L, Tensor M1, Tensor M2, Tensor R, Tensor(a!) out, Tensor flags, "
+              "int n_chunks, int epoch) -> ()")
     tl.define("push_shard(Tensor src, int[] dst_ptrs, int[] flag_ptrs, int epoch, Tensor(a!) ticket) -> ()")
     tl.define("env_left(Tensor env, Tensor M, Tensor site, Tensor(a!) out) -> ()")
     tl.define("env_right(Tensor env, Tensor M, Tensor site, Tensor(a!) out) -> ()")
@@ -476,6 +496,7 @@ def register_ops() -> None:
               "int norm_idx, int flags, Tensor(c!) scratch) -> ()")
     tl.impl("heff_apply", _impl_heff_apply, "CUDA")
     tl.impl("heff_apply_gated", _impl_heff_apply_gated, "CUDA")
+    tl.impl("heff_apply_colgated", _impl_heff_apply_colgated, "CUDA")
     tl.impl("push_shard", _impl_push_shard, "CUDA")
     tl.impl("env_left", _impl_env_left, "CUDA")
     tl.impl("env_right", _impl_env_right, "CUDA")

@@ -35,6 +35,7 @@ struct GemmArgs {
     int force_path;                 // 0 auto, 1 TMA, 2 cp.async
     // optional k-chunk gating (TMA path only): see TArgs in gemm_tma.cu
     int ksplit = 1, krot = 0, kepoch = 0, klocal = 0;
+    int nsplit = 1;                 // > 1: gate whole tiles on the arrival of their COLUMN block of B
     const int* kflags = nullptr;
 };
 int gemm_launch(const GemmArgs& g, cudaStream_t stream);

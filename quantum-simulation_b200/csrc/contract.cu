@@ -383,8 +383,9 @@ extern "C" int qsb_heff_apply(const qsb_heff_desc* d, void* stream_) {
     g1.force_path = 0;
     if (d->n_chunks > 1) {           // fused all-gather -> GEMM: gate the k chunks on their arrival flags
         if (!d->chunk_flags) return QSB_ERR_ARG;
-        g1.ksplit = d->n_chunks; g1.krot = d->chunk_rot; g1.kepoch = d->chunk_epoch; g1.kflags = d->chunk_flags;
-        g1.klocal = d->chunk_local;
+        g1.kepoch = d->chunk_epoch; g1.kflags = d->chunk_flags;
+        if (d->chunk_axis == 1) { g1.nsplit = d->n_chunks; }
+        else { g1.ksplit = d->n_chunks; g1.krot = d->chunk_rot; g1.klocal = d->chunk_local; }
         g1.force_path = 1;
     }
     if ((rc = gemm_launch(g1, stream))) return rc;
@@ -495,6 +496,23 @@ extern "C" int qsb_push_shard_dma(const void* src, size_t bytes, void* const* ds
         int rc = check_cuda(cudaMemcpyAsync(dst[i], src, bytes, cudaMemcpyDefault, stream));   // peer, local or pinned host source
         if (rc) return rc;
         if (wv((CUstream)stream, (CUdeviceptr)flag[i], (cuuint32_t)epoch, 0) != CUDA_SUCCESS) return QSB_ERR_LAUNCH;
+    }
+    return QSB_OK;
+}
+
+extern "C" int qsb_upload_columns(const void* src_host, void* dst, int64_t rows, int64_t row_elems, int elem_bytes,
+                                  int n_chunks, int* flags, int epoch, void* stream_) {
+    if (!src_host || !dst || !flags || rows < 1 || row_elems < 1 || n_chunks < 1 || elem_bytes < 1) return QSB_ERR_ARG;
+    if (row_elems % n_chunks != 0) return QSB_ERR_SHAPE;
+    WriteValue32Fn wv = get_write_value32();
+    if (!wv) return QSB_ERR_DEVICE;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const size_t pitch = (size_t)row_elems * elem_bytes, width = pitch / n_chunks;
+    for (int c = 0; c < n_chunks; ++c) {
+        int rc = check_cuda(cudaMemcpy2DAsync((char*)dst + c * width, pitch, (const char*)src_host + c * width, pitch,
+                                              width, (size_t)rows, cudaMemcpyDefault, stream));
+        if (rc) return rc;
+        if (wv((CUstream)stream, (CUdeviceptr)(flags + c), (cuuint32_t)epoch, 0) != CUDA_SUCCESS) return QSB_ERR_LAUNCH;
     }
     return QSB_OK;
 }

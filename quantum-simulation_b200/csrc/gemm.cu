@@ -297,7 +297,7 @@ int gemm_launch(const GemmArgs& g, cudaStream_t stream) {
         if (used) return QSB_OK;
         if (g.force_path == 1) return QSB_ERR_STRIDE;
     }
-    if (g.ksplit > 1) return QSB_ERR_STRIDE;     // chunk gating needs the TMA-staged kernel
+    if (g.ksplit > 1 || g.nsplit > 1) return QSB_ERR_STRIDE;     // chunk gating needs the TMA-staged kernel
 
     KArgs k;
     k.M = g.M; k.N = g.N; k.K = g.K; k.P = g.P;

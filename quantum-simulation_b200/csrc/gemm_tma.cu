@@ -45,6 +45,7 @@ struct TArgs {
     // kflags[c] >= kepoch (set by the peer that pushed it); chunks are visited starting from chunk krot
     int raster;                 // tile rows per rasterisation group
     int ksplit, krot, kepoch, klocal;    // klocal: chunk krot is already in place, never wait for it
+    int nsplit;                          // > 1: whole tiles are gated on the column block of B they read (kflags)
     const int* kflags;
 };
 
@@ -217,7 +218,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 
     // ---- producer (thread 0): walks the same segment sequence as the consumers, S-2 stages ahead
     constexpr int KMUL = CPLX ? 2 : 1;       // innermost TMA coordinate is in float64 units
-    Sched ps; ps.init(sk.U_sk, sk.ipt, sk.T_sk, sk.dp_waves, G, cta, g.ksplit > 1);
+    Sched ps; ps.init(sk.U_sk, sk.ipt, sk.T_sk, sk.dp_waves, G, cta, g.ksplit > 1 || g.nsplit > 1);
     int p_tile = -1, p_it = 0, p_it1 = 0, p_m0 = 0, p_n0 = 0, p_z = 0;
     int pj = 0;                              // CTA-local index of the next k-iteration to issue
     int p_chunk_ok = -1;                     // last gated k chunk known to have arrived
@@ -228,6 +229,19 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             int tm, tn;
             tile_coords(p_tile, g.tiles_m, g.tiles_n, tm, tn, p_z, g.raster);
             p_m0 = tm * C::BM; p_n0 = tn * C::BN;
+            if (g.nsplit > 1) {              // column-block gating: this tile reads one block of B, wait for it once
+                const int c = (int)((long long)p_n0 * g.nsplit / g.N);
+                if (c != p_chunk_ok) {
+                    int v;
+                    const long long t0 = clock64();
+                    do {
+                        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(g.kflags + c) : "memory");
+                        if (v < g.kepoch && clock64() - t0 > 100000000000LL) __trap();
+                    } while (v < g.kepoch);
+                    asm volatile("fence.proxy.async.global;" ::: "memory");
+                    p_chunk_ok = c;
+                }
+            }
         }
         const int slot = pj % S;
         if (pj >= S) mbar_wait_spin(bar_empty + 8 * slot, ((pj / S) + 1) & 1);
@@ -264,7 +278,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     FragAddr<CPLX, A_KC> fa; fa.init(wm0, g8, t4);
     FragAddr<CPLX, B_KC> fb; fb.init(wn0, g8, t4);
 
-    Sched cs; cs.init(sk.U_sk, sk.ipt, sk.T_sk, sk.dp_waves, G, cta, g.ksplit > 1);
+    Sched cs; cs.init(sk.U_sk, sk.ipt, sk.T_sk, sk.dp_waves, G, cta, g.ksplit > 1 || g.nsplit > 1);
     int tile, it0, it1;
     int cj = 0;                              // CTA-local index of the k-iteration being consumed
     double* my_partial = sk.partial + (size_t)cta * kAccPerThread * kTmaThreads + tid;
@@ -587,11 +601,15 @@ int gemm_tma_try(const GemmArgs& g, cudaStream_t stream, bool* used) {
         if (raster_env < 0) { const char* e = getenv("QSB_RASTER_GROUP"); raster_env = e ? atoi(e) : 0; }
         t.raster = raster_env > 0 ? raster_env : kRasterGroup;
     }
-    t.ksplit = 1; t.krot = 0; t.kepoch = 0; t.klocal = 0; t.kflags = nullptr;
+    t.ksplit = 1; t.krot = 0; t.kepoch = 0; t.klocal = 0; t.kflags = nullptr; t.nsplit = 1;
     if (g.ksplit > 1) {
         const int ktiles = (g.K + BK - 1) / BK;
         if (g.P != 1 || g.K % BK != 0 || ktiles % g.ksplit != 0 || !g.kflags) return QSB_ERR_STRIDE;
         t.ksplit = g.ksplit; t.krot = g.krot % g.ksplit; t.kepoch = g.kepoch; t.kflags = g.kflags; t.klocal = g.klocal;
+    }
+    if (g.nsplit > 1) {                  // tiles must not straddle column blocks
+        if (!g.kflags || g.N % g.nsplit != 0 || (g.N / g.nsplit) % BN != 0) return QSB_ERR_STRIDE;
+        t.nsplit = g.nsplit; t.kepoch = g.kepoch; t.kflags = g.kflags;
     }
     int rc;
     if (cplx) {

@@ -152,10 +152,13 @@ class ApplyMPO(_BaseContractModule):
 
     def _forward_host(self, psi_host: torch.Tensor, L, M1, M2, R, out_host: Optional[torch.Tensor]) -> torch.Tensor:
         """``psi_flat`` (and ``out``) in PINNED HOST memory, L / M / R on the GPU: the upload of theta, the matvec
-        and the download of the result are pipelined instead of serialised.  theta goes up in k-chunks on a copy
-        stream, each followed by a stream-ordered flag write, and the step-1 GEMM is gated per chunk (the same
-        mechanism as the multi-GPU fused exchange); the matvec runs in row blocks of the left bond and each finished
-        block is downloaded on a second copy stream while the next one computes.  Compute stays on the GPU -- this is
+        and the download of the result are pipelined instead of serialised.  theta, viewed as a (chi_l, d1 d2 chi_r)
+        matrix, goes up in COLUMN blocks on a copy stream (qsb_upload_columns), each followed by a stream-ordered
+        flag write; an output tile of the step-1 GEMM reads exactly one column block and is gated on its flag, so
+        compute starts after 1/8 of the upload (row-block / k-chunk gating, the mechanism of the multi-GPU fused
+        exchange, is the fallback when the column blocks do not align with the tiles).  The matvec runs in row
+        blocks of the left bond and each finished block is downloaded on a second copy stream while the next one
+        computes.  Compute stays on the GPU -- this is
         not a CPU fallback; unpinned host tensors are rejected."""
         L, M1, M2, R = (_dev_tensor(t) for t in (L, M1, M2, R))
         M1, M2 = M1.contiguous(), M2.contiguous()
@@ -186,10 +189,17 @@ class ApplyMPO(_BaseContractModule):
             if buf is None or buf.numel() < numel or buf.dtype != dt:
                 pipe[key] = torch.empty(numel, dtype=dt, device=dev)
         theta_dev, out_dev = pipe["theta"][:n_in], pipe["out"][:n_out]
-        bk = 8 if dt.is_complex else 16
-        n_chunks = 8
-        while n_chunks > 1 and (chi_li % (bk * n_chunks) != 0):
-            n_chunks //= 2
+        bk, bn = (8, 64) if dt.is_complex else (16, 128)
+        N1 = n_in // chi_li                               # theta as a (chi_l, d1 d2 chi_r) matrix
+        # preferred: COLUMN blocks of theta -- an output tile of step 1 needs one block only, so the first tiles start
+        # after 1/8 of the upload; fallback: ROW blocks (k chunks), then a plain upload
+        col_chunks = 8
+        while col_chunks > 1 and (N1 % col_chunks != 0 or (N1 // col_chunks) % bn != 0):
+            col_chunks //= 2
+        row_chunks = 8
+        while row_chunks > 1 and (chi_li % (bk * row_chunks) != 0):
+            row_chunks //= 2
+        mode = "col" if col_chunks > 1 else ("row" if row_chunks > 1 else "plain")
         n_blocks = 4
         while n_blocks > 1 and (chi_lo % n_blocks != 0 or chi_lo // n_blocks < 128):
             n_blocks //= 2
@@ -198,30 +208,35 @@ class ApplyMPO(_BaseContractModule):
         with torch.cuda.device(dev):
             pipe["h2d"].wait_stream(main)                  # the staging buffers are free once earlier work is done
             pipe["d2h"].wait_stream(main)
-            if n_chunks > 1:
-                pipe["epoch"] += 1
-                epoch = pipe["epoch"]
-                chunk = n_in // n_chunks
-                with torch.cuda.stream(pipe["h2d"]):
-                    for c in range(n_chunks):
+            pipe["epoch"] += 1
+            epoch = pipe["epoch"]
+            with torch.cuda.stream(pipe["h2d"]):
+                if mode == "col":
+                    _lib.upload_columns(psi_host, theta_dev, chi_li, N1, col_chunks, pipe["flags"], epoch)
+                elif mode == "row":
+                    chunk = n_in // row_chunks
+                    for c in range(row_chunks):
                         _lib.push_shard_dma(psi_host[c * chunk:(c + 1) * chunk],
                                             [theta_dev.data_ptr() + c * chunk * es],
                                             [pipe["flags"].data_ptr() + 4 * c], epoch)
-            else:
-                with torch.cuda.stream(pipe["h2d"]):
+                else:
                     theta_dev.copy_(psi_host, non_blocking=True)
+            if mode == "plain":
                 main.wait_stream(pipe["h2d"])
             rows = chi_lo // n_blocks
             out_h = out_host.view(-1)
             for b in range(n_blocks):
                 Lb = L[:, b * rows:(b + 1) * rows, :]
                 ob = out_dev[b * rows * per_out:(b + 1) * rows * per_out]
-                if n_chunks > 1:
+                if mode != "plain":
                     try:
-                        _lib.ops.heff_apply_gated(theta_dev, Lb, M1, M2, R, ob, pipe["flags"], n_chunks, 0, epoch, 0)
+                        if mode == "col":
+                            _lib.ops.heff_apply_colgated(theta_dev, Lb, M1, M2, R, ob, pipe["flags"], col_chunks, epoch)
+                        else:
+                            _lib.ops.heff_apply_gated(theta_dev, Lb, M1, M2, R, ob, pipe["flags"], row_chunks, 0, epoch, 0)
                     except ValueError:                     # operands the TMA-staged (gated) GEMM cannot describe
                         main.wait_stream(pipe["h2d"])
-                        n_chunks = 1
+                        mode = "plain"
                         _lib.ops.heff_apply(theta_dev, Lb, M1, M2, R, ob)
                 else:
                     _lib.ops.heff_apply(theta_dev, Lb, M1, M2, R, ob)
