@@ -372,6 +372,8 @@ def run_ours(args):
     e2e = {"value": flops_total / (sec_e / Ke) / 1e9, "unit": UNIT, "h2d_bytes_per_step": n * es,
            "d2h_bytes_per_step": n * es, "ms_per_step": sec_e / Ke * 1e3, "steps": Ke,
            "bytes_note": "whole-job bytes per step, summed over ranks (each rank moves 1/N of them)",
+           "host_pipeline_mode": (next(iter(qsb.ApplyMPO._host_pipes.values()), {}).get("last_mode")
+                                  if world == 1 else None),
            "call": ("quantum_simulation_b200.ApplyMPO.forward(pinned host psi, out=pinned host) -- chunked upload gating "
                     "the step-1 GEMM, row-block download overlapped" if world == 1 else
                     "quantum_simulation_b200.parallel.FusedShardedApplyMPO / ShardedApplyMPO")

@@ -46,6 +46,7 @@ struct TArgs {
     int raster;                 // tile rows per rasterisation group
     int ksplit, krot, kepoch, klocal;    // klocal: chunk krot is already in place, never wait for it
     int nsplit;                          // > 1: whole tiles are gated on the column block of B they read (kflags)
+    int Zb;                              // batch count (needed for the n-outermost tile order of nsplit mode)
     const int* kflags;
 };
 
@@ -172,6 +173,20 @@ struct Sched {
     }
 };
 
+// tile index -> (tm, tn, z).  Default: batch z outermost, grouped rasterisation inside (L2-friendly).  Column-gated
+// mode: n outermost (then z, then m), so tiles are visited in the order their column block of B arrives.
+__device__ __forceinline__ void tile_map(const TArgs& g, int tile, int& tm, int& tn, int& z) {
+    if (g.nsplit > 1) {
+        const int per_n = g.tiles_m * g.Zb;
+        tn = tile / per_n;
+        const int r = tile - tn * per_n;
+        z = r / g.tiles_m;
+        tm = r - z * g.tiles_m;
+    } else {
+        tile_map(g, tile, tm, tn, z);
+    }
+}
+
 struct SkArgs {
     long long U_sk;             // stream-K units
     int T_sk, dp_waves, ipt;
@@ -218,7 +233,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 
     // ---- producer (thread 0): walks the same segment sequence as the consumers, S-2 stages ahead
     constexpr int KMUL = CPLX ? 2 : 1;       // innermost TMA coordinate is in float64 units
-    Sched ps; ps.init(sk.U_sk, sk.ipt, sk.T_sk, sk.dp_waves, G, cta, g.ksplit > 1 || g.nsplit > 1);
+    Sched ps; ps.init(sk.U_sk, sk.ipt, sk.T_sk, sk.dp_waves, G, cta, g.ksplit > 1);
     int p_tile = -1, p_it = 0, p_it1 = 0, p_m0 = 0, p_n0 = 0, p_z = 0;
     int pj = 0;                              // CTA-local index of the next k-iteration to issue
     int p_chunk_ok = -1;                     // last gated k chunk known to have arrived
@@ -227,7 +242,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         if (p_it == p_it1) {
             if (!p_more || !ps.next(p_tile, p_it, p_it1)) { p_more = false; return; }
             int tm, tn;
-            tile_coords(p_tile, g.tiles_m, g.tiles_n, tm, tn, p_z, g.raster);
+            tile_map(g, p_tile, tm, tn, p_z);
             p_m0 = tm * C::BM; p_n0 = tn * C::BN;
             if (g.nsplit > 1) {              // column-block gating: this tile reads one block of B, wait for it once
                 const int c = (int)((long long)p_n0 * g.nsplit / g.N);
@@ -278,7 +293,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     FragAddr<CPLX, A_KC> fa; fa.init(wm0, g8, t4);
     FragAddr<CPLX, B_KC> fb; fb.init(wn0, g8, t4);
 
-    Sched cs; cs.init(sk.U_sk, sk.ipt, sk.T_sk, sk.dp_waves, G, cta, g.ksplit > 1 || g.nsplit > 1);
+    Sched cs; cs.init(sk.U_sk, sk.ipt, sk.T_sk, sk.dp_waves, G, cta, g.ksplit > 1);
     int tile, it0, it1;
     int cj = 0;                              // CTA-local index of the k-iteration being consumed
     double* my_partial = sk.partial + (size_t)cta * kAccPerThread * kTmaThreads + tid;
@@ -400,7 +415,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         }
         // store: lane owns rows frag_index<A>(i, g8) and columns frag_index<B>(j, 2*t4), frag_index<B>(j, 2*t4+1)
         int tm, tn, z;
-        tile_coords(tile, g.tiles_m, g.tiles_n, tm, tn, z, g.raster);
+        tile_map(g, tile, tm, tn, z);
         const int m0 = tm * C::BM, n0 = tn * C::BN;
         char* Cz = g.C + g.c_zs * z * C::ES;
         bool vec_ok = false;
@@ -601,7 +616,7 @@ int gemm_tma_try(const GemmArgs& g, cudaStream_t stream, bool* used) {
         if (raster_env < 0) { const char* e = getenv("QSB_RASTER_GROUP"); raster_env = e ? atoi(e) : 0; }
         t.raster = raster_env > 0 ? raster_env : kRasterGroup;
     }
-    t.ksplit = 1; t.krot = 0; t.kepoch = 0; t.klocal = 0; t.kflags = nullptr; t.nsplit = 1;
+    t.ksplit = 1; t.krot = 0; t.kepoch = 0; t.klocal = 0; t.kflags = nullptr; t.nsplit = 1; t.Zb = g.Z;
     if (g.ksplit > 1) {
         const int ktiles = (g.K + BK - 1) / BK;
         if (g.P != 1 || g.K % BK != 0 || ktiles % g.ksplit != 0 || !g.kflags) return QSB_ERR_STRIDE;

@@ -245,6 +245,7 @@ class ApplyMPO(_BaseContractModule):
                 pipe["d2h"].wait_event(done)
                 with torch.cuda.stream(pipe["d2h"]):
                     out_h[b * rows * per_out:(b + 1) * rows * per_out].copy_(ob, non_blocking=True)
+            pipe["last_mode"] = mode
             main.wait_stream(pipe["d2h"])                  # the result is on the host once `main` gets here
             main.wait_stream(pipe["h2d"])
         return out_host
