@@ -175,15 +175,17 @@ struct Sched {
 
 // tile index -> (tm, tn, z).  Default: batch z outermost, grouped rasterisation inside (L2-friendly).  Column-gated
 // mode: n outermost (then z, then m), so tiles are visited in the order their column block of B arrives.
-__device__ __forceinline__ void tile_map(const TArgs& g, int tile, int& tm, int& tn, int& z) {
-    if (g.nsplit > 1) {
-        const int per_n = g.tiles_m * g.Zb;
+template <bool GATED>
+__device__ __forceinline__ void tile_map(int nsplit, int tiles_m, int tiles_n, int Zb, int raster, int tile,
+                                         int& tm, int& tn, int& z) {
+    if (GATED && nsplit > 1) {
+        const int per_n = tiles_m * Zb;
         tn = tile / per_n;
         const int r = tile - tn * per_n;
-        z = r / g.tiles_m;
-        tm = r - z * g.tiles_m;
+        z = r / tiles_m;
+        tm = r - z * tiles_m;
     } else {
-        tile_map(g, tile, tm, tn, z);
+        tile_coords(tile, tiles_m, tiles_n, tm, tn, z, raster);
     }
 }
 
@@ -196,7 +198,9 @@ struct SkArgs {
 };
 constexpr int kAccPerThread = 64;
 
-template <bool CPLX, bool A_KC, bool B_KC>
+// GATED instantiations carry the arrival-gating code (fused multi-GPU exchange, host upload); the plain ones do
+// not: the kernel sits at the register limit and any extra live value perturbs the main loop (measured: 3 %).
+template <bool CPLX, bool A_KC, bool B_KC, bool GATED>
 __global__ void __launch_bounds__(kTmaThreads, 1)
 gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TArgs g,
                 const SkArgs sk) {
@@ -233,7 +237,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 
     // ---- producer (thread 0): walks the same segment sequence as the consumers, S-2 stages ahead
     constexpr int KMUL = CPLX ? 2 : 1;       // innermost TMA coordinate is in float64 units
-    Sched ps; ps.init(sk.U_sk, sk.ipt, sk.T_sk, sk.dp_waves, G, cta, g.ksplit > 1);
+    Sched ps; ps.init(sk.U_sk, sk.ipt, sk.T_sk, sk.dp_waves, G, cta, GATED && g.ksplit > 1);
     int p_tile = -1, p_it = 0, p_it1 = 0, p_m0 = 0, p_n0 = 0, p_z = 0;
     int pj = 0;                              // CTA-local index of the next k-iteration to issue
     int p_chunk_ok = -1;                     // last gated k chunk known to have arrived
@@ -242,9 +246,9 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         if (p_it == p_it1) {
             if (!p_more || !ps.next(p_tile, p_it, p_it1)) { p_more = false; return; }
             int tm, tn;
-            tile_map(g, p_tile, tm, tn, p_z);
+            tile_map<GATED>(g.nsplit, g.tiles_m, g.tiles_n, g.Zb, g.raster, p_tile, tm, tn, p_z);
             p_m0 = tm * C::BM; p_n0 = tn * C::BN;
-            if (g.nsplit > 1) {              // column-block gating: this tile reads one block of B, wait for it once
+            if (GATED && g.nsplit > 1) {     // column-block gating: this tile reads one block of B, wait for it once
                 const int c = (int)((long long)p_n0 * g.nsplit / g.N);
                 if (c != p_chunk_ok) {
                     int v;
@@ -261,7 +265,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         const int slot = pj % S;
         if (pj >= S) mbar_wait_spin(bar_empty + 8 * slot, ((pj / S) + 1) & 1);
         int p = p_it / ktiles, k0 = (p_it - p * ktiles) * C::BK;
-        if (g.ksplit > 1) {                  // P == 1 here: visit the k chunks in rotated order, gated on arrival
+        if (GATED && g.ksplit > 1) {         // P == 1 here: visit the k chunks in rotated order, gated on arrival
             const int per = ktiles / g.ksplit;
             const int c = p_it / per;
             int kc = c + g.krot; if (kc >= g.ksplit) kc -= g.ksplit;
@@ -293,7 +297,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     FragAddr<CPLX, A_KC> fa; fa.init(wm0, g8, t4);
     FragAddr<CPLX, B_KC> fb; fb.init(wn0, g8, t4);
 
-    Sched cs; cs.init(sk.U_sk, sk.ipt, sk.T_sk, sk.dp_waves, G, cta, g.ksplit > 1);
+    Sched cs; cs.init(sk.U_sk, sk.ipt, sk.T_sk, sk.dp_waves, G, cta, GATED && g.ksplit > 1);
     int tile, it0, it1;
     int cj = 0;                              // CTA-local index of the k-iteration being consumed
     double* my_partial = sk.partial + (size_t)cta * kAccPerThread * kTmaThreads + tid;
@@ -415,7 +419,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         }
         // store: lane owns rows frag_index<A>(i, g8) and columns frag_index<B>(j, 2*t4), frag_index<B>(j, 2*t4+1)
         int tm, tn, z;
-        tile_map(g, tile, tm, tn, z);
+        tile_map<GATED>(g.nsplit, g.tiles_m, g.tiles_n, g.Zb, g.raster, tile, tm, tn, z);
         const int m0 = tm * C::BM, n0 = tn * C::BN;
         char* Cz = g.C + g.c_zs * z * C::ES;
         bool vec_ok = false;
@@ -543,10 +547,10 @@ static int sk_scratch(SkScratch** out) {
     return QSB_OK;
 }
 
-template <bool CPLX, bool A_KC, bool B_KC>
-static int launch_tma(const CUtensorMap& ma, const CUtensorMap& mb, const TArgs& t, int Z, cudaStream_t stream) {
+template <bool CPLX, bool A_KC, bool B_KC, bool GATED>
+static int launch_tma_g(const CUtensorMap& ma, const CUtensorMap& mb, const TArgs& t, int Z, cudaStream_t stream) {
     using C = TCfg<CPLX>;
-    auto kern = gemm_tma_kernel<CPLX, A_KC, B_KC>;
+    auto kern = gemm_tma_kernel<CPLX, A_KC, B_KC, GATED>;
     constexpr int SMEM = C::STAGES * (C::BM + C::BN) * C::BK * C::ES + 2 * C::STAGES * 8 + 1024;
     static bool configured[64] = {};         // per instantiation and device (the attribute is per device)
     int dev = 0;
@@ -582,6 +586,12 @@ static int launch_tma(const CUtensorMap& ma, const CUtensorMap& mb, const TArgs&
     kern<<<(unsigned)G, kTmaThreads, SMEM, stream>>>(ma, mb, t, sk);
     ++g_count_tma;
     return check_launch();
+}
+
+template <bool CPLX, bool A_KC, bool B_KC>
+static int launch_tma(const CUtensorMap& ma, const CUtensorMap& mb, const TArgs& t, int Z, cudaStream_t stream) {
+    if (t.ksplit > 1 || t.nsplit > 1) return launch_tma_g<CPLX, A_KC, B_KC, true>(ma, mb, t, Z, stream);
+    return launch_tma_g<CPLX, A_KC, B_KC, false>(ma, mb, t, Z, stream);
 }
 
 int gemm_tma_try(const GemmArgs& g, cudaStream_t stream, bool* used) {
