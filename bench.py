@@ -2,6 +2,7 @@
 """Benchmark of the two-site DMRG hot path on B200 (BASELINE.json metric).
 
     python bench.py --gpus N --steps K --warmup W [--impl reference] [--chi 2048] [--dtype f64|c128]
+                    [--model heis|j1j2|hubbard|tfim] [--exchange auto|fused|nccl] [--no-extras]
 
 Workload (config.workload): BASELINE config 3 -- Heisenberg chain L=100, chi=2048, the bulk bond (sites 50|51),
 MPO bond W=5, d=2.  A *step* is one H_eff matvec  out = L . M1 . M2 . R . theta  (reference
@@ -9,8 +10,10 @@ quantum_simulation/dmrg.py:178-228, the operator Lanczos applies 8x per bond upd
 
   value        whole-job matvec throughput in GFLOP/s with every input resident in HBM, counted with the dense
                ncon-order flop count the reference executes (qsb_heff_flops)
-  e2e          the same metric through the reference-facing call ``ApplyMPO.forward`` with theta in pinned HOST
-               memory: H2D copy of theta + matvec + D2H copy of the result inside the timed region
+  e2e          the same metric through the reference-facing call ``ApplyMPO.forward`` with theta AND the result in
+               pinned HOST memory: upload of theta + matvec + download of the result inside the timed region (the
+               call pipelines them: column-block upload gating the step-1 GEMM, row-block download overlapped);
+               N > 1: every rank uploads its shard and downloads its rows
   roofline     the dominant kernel (the FP64 tensor-core GEMM of step 1), timed with CUDA events recorded on the
                launching stream inside the timed region (qsb_heff_set_stage_events); peak = FP64 tensor-pipe
                issue rate measured in this run by the register-resident DMMA probe (MEASURED_PEAKS.json has no
@@ -19,8 +22,10 @@ quantum_simulation/dmrg.py:178-228, the operator Lanczos applies 8x per bond upd
   cpu_baseline the oracle (torch-CPU restatement of the reference's ncon path) timed on the host cores
   lanczos / env_update   the other hot-path kernels: achieved HBM GB/s of the fused vector ops, env-update GFLOP/s
 
-N > 1: the matvec is sharded over the left bond index a' (rows of L and of the result); every step all-gathers
-theta across the ranks (NCCL) and runs the local row block -- strong scaling of the same chi.
+N > 1: the matvec is sharded over the left bond index a' (rows of L and of the result); every step exchanges the
+theta shards -- by default fused into the matvec (P2P copy-engine pushes + arrival-gated step-1 GEMM, no NCCL on the
+data path; ``--exchange nccl`` = all-gather then matvec) -- and runs the local row block: strong scaling of the same
+chi.  ``--model`` selects the MPO bond of another BASELINE config (j1j2 = config 4, hubbard = config 5, tfim = 2).
 ``--impl reference`` times the oracle on the host cores (rank 0 only) for the same config.
 """
 import argparse
