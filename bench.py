@@ -208,7 +208,7 @@ def workload_config(args, world):
     return {"workload": f"{desc}, chi={args.chi}, bulk bond {site}|{site + 1}, MPO bonds "
                         f"{M1.shape[0]}-{M1.shape[1]}-{M2.shape[1]}, d={M1.shape[2]}, "
                         f"{'float64' if args.dtype == 'f64' else 'complex128'}; one H_eff matvec per step",
-            "chi": args.chi, "d": int(M1.shape[2]), "W": int(M1.shape[0]), "model": args.model,
+            "chi": args.chi, "d": int(M1.shape[2]), "W": int(M1.shape[0]), "hamiltonian": args.model,
             "parallelism": "single GPU" if world == 1 else f"left-bond row shards x{world}",
             "l2_policy": "inputs + intermediates per step (>1 GB at chi=2048) exceed the 126 MB L2; no flush needed"}
 
