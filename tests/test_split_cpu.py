@@ -1,0 +1,73 @@
+"""The two-site split (svd.py) is plain torch and device-agnostic: its Gram/eigh path is checked on the CPU against
+torch.linalg.svd and the reference's truncation rule (dmrg.py:687-695)."""
+import pytest
+import torch
+
+from quantum_simulation_b200.svd import two_site_split, _keep_from_spectrum
+
+
+def _matrix(m, n, dtype, decay, seed):
+    g = torch.Generator().manual_seed(seed)
+    r = min(m, n)
+    U0, _ = torch.linalg.qr(torch.randn(m, r, dtype=dtype, generator=g))
+    V0, _ = torch.linalg.qr(torch.randn(n, r, dtype=dtype, generator=g))
+    s = torch.exp(-torch.arange(r, dtype=torch.float64) * decay)
+    return (U0 * s.to(dtype)) @ V0.conj().T, s
+
+
+def _reference_keep(S, maxdim, cutoff):
+    keep_max = min(S.numel(), maxdim)
+    keep_cut = S.numel()
+    if cutoff > 0.0:
+        S2 = S ** 2
+        cs = torch.cumsum(S2 / torch.sum(S2), dim=0)
+        keep_cut = int(torch.searchsorted(cs, 1.0 - cutoff, right=True)) + 1
+    return max(1, min(keep_max, keep_cut))
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.complex128])
+@pytest.mark.parametrize("shape", [(96, 96), (64, 160), (160, 64), (1, 8), (8, 1), (2, 2)])
+@pytest.mark.parametrize("maxdim,cutoff", [(10 ** 6, 0.0), (24, 0.0), (10 ** 6, 1e-10), (5, 1e-6)])
+def test_gram_split_matches_svd(dtype, shape, maxdim, cutoff):
+    m, n = shape
+    theta, _ = _matrix(m, n, dtype, 0.2, seed=m * 1000 + n)
+    U, S, Vh, keep = two_site_split(theta, maxdim, cutoff, fast_min=1)          # force the Gram/eigh path
+    Ue, Se, Vhe = torch.linalg.svd(theta, full_matrices=False)
+    assert keep == _reference_keep(Se, maxdim, cutoff) == _keep_from_spectrum(Se, maxdim, cutoff)
+    assert U.shape == (m, keep) and Vh.shape == (keep, n) and S.shape == Se.shape
+    eye = torch.eye(keep, dtype=dtype)
+    assert float(torch.linalg.norm(U.conj().T @ U - eye)) < 1e-12
+    assert float(torch.linalg.norm(Vh @ Vh.conj().T - eye)) < 1e-12
+    # S_i = sqrt(eigenvalue): absolute accuracy eps * S_max^2 / S_i (documented in svd.py), i.e. exact to ~1e-15 at
+    # the top of the spectrum, relative 1e-4 for S_i / S_max = 1e-6, noise below sqrt(eps) * S_max
+    top = Se > 1e-7 * Se[0]
+    assert bool(((S - Se).abs()[top] <= 2e-14 * Se[0] ** 2 / Se[top]).all())
+    assert float((S[:4] - Se[:4]).abs().max()) <= 1e-13 * float(Se[0])
+    rec = (U * S[:keep].to(dtype)) @ Vh
+    best = (Ue[:, :keep] * Se[:keep].to(dtype)) @ Vhe[:keep]
+    assert float(torch.linalg.norm(rec - best)) < 5e-8 * float(Se[0])
+    # the small-block path is torch.linalg.svd itself
+    U2, S2, Vh2, keep2 = two_site_split(theta, maxdim, cutoff, fast_min=10 ** 9)
+    assert keep2 == keep and torch.allclose(S2, Se)
+
+
+def test_gram_split_rank_deficient_and_degenerate():
+    """Exactly degenerate and exactly zero singular values (product states, symmetry multiplets): still isometric
+    factors and the right weights; the arbitrary rotation inside a degenerate multiplet does not matter."""
+    g = torch.Generator().manual_seed(3)
+    Q1, _ = torch.linalg.qr(torch.randn(40, 40, dtype=torch.float64, generator=g))
+    Q2, _ = torch.linalg.qr(torch.randn(48, 40, dtype=torch.float64, generator=g))
+    s = torch.tensor([1.0] * 3 + [0.5] * 4 + [0.0] * 33, dtype=torch.float64)
+    theta = (Q1 * s) @ Q2.T
+    U, S, Vh, keep = two_site_split(theta, 7, 0.0, fast_min=1)
+    assert keep == 7
+    assert torch.allclose(S[:7], s[:7], atol=1e-12) and float(S[7:].max()) < 1e-7
+    assert float(torch.linalg.norm(U.T @ U - torch.eye(7, dtype=torch.float64))) < 1e-12
+    assert float(torch.linalg.norm(Vh @ Vh.T - torch.eye(7, dtype=torch.float64))) < 1e-12
+    assert float(torch.linalg.norm((U * S[:7]) @ Vh - theta)) < 1e-12
+    U, S, Vh, keep = two_site_split(theta, 100, 1e-12, fast_min=1)              # cutoff drops the numerical zeros
+    assert keep == 7
+    rank1 = torch.outer(Q1[:, 0], Q2[:, 0])
+    U, S, Vh, keep = two_site_split(rank1, 4, 0.0, fast_min=1)
+    assert keep == 4 and abs(float(S[0]) - 1.0) < 1e-12
+    assert float(torch.linalg.norm(U.T @ U - torch.eye(4, dtype=torch.float64))) < 1e-12
