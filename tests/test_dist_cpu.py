@@ -148,12 +148,11 @@ def _dmrg_worker(rank, world, port, dtype_name, result_q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("dtype_name", ["float64", "complex128"])
-def test_sharded_dmrg_world2_matches_unsharded(dtype_name):
+@pytest.mark.parametrize("dtype_name,world", [("float64", 2), ("complex128", 2), ("float64", 4)])
+def test_sharded_dmrg_matches_unsharded(dtype_name, world):
     """Full two-site DMRG (2 sweeps, Heisenberg L=20, chi=16) through ShardedDMRG on 2 gloo ranks: row-sharded
     environments, sharded Lanczos, reduce-scatter env updates, broadcast split -- per-update energies equal the
     unsharded run to 1e-10 relative and every rank ends with the same energy."""
-    world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
@@ -176,7 +175,7 @@ def test_sharded_dmrg_world2_matches_unsharded(dtype_name):
         assert rel <= 1e-10, f"rank {rank}: max relative deviation {rel:.2e}"
         assert comm["sharded_steps"] > 0 and comm["replicated_steps"] > 0
         assert comm["reduce_scatter_env"] > 0 and comm["all_gather_env"] > 0 and comm["broadcast_split"] > 0
-    assert res[0][5] == res[1][5]
+    assert len({r[5] for r in res}) == 1
 
 
 def test_row_partition():
