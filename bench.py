@@ -60,6 +60,7 @@ def parse():
                     help="which BASELINE config's MPO bond to run (default: config 3, the headline)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "fused", "nccl"],
                     help="N>1: how theta shards are exchanged (auto = fused P2P push if available, else NCCL)")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the measured full DMRG sweep of the extras leg")
     ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / lanczos / env / library legs")
     return ap.parse_args()
 
@@ -522,6 +523,42 @@ def extras(args, qsb, _lib, dev, dtype, L, M1, M2, R, theta, peak_tf):
             torch.cuda.empty_cache()
     except Exception as ex:
         out["complex128_same_config"] = {"error": repr(ex)[:200]}
+    # (3d) the other half of BASELINE.json's metric: one FULL two-site DMRG sweep, measured (Heisenberg config only)
+    if args.model == "heis" and not args.no_sweep:
+        try:
+            import contextlib
+            import io
+            Lsites = 100
+            del L, R, theta
+            _lib.release_workspaces()
+            qsb.clear_workspaces()
+            torch.cuda.empty_cache()
+            with contextlib.redirect_stdout(io.StringIO()):
+                t0 = time.perf_counter()
+                mps = qsb.MPS(Lsites, 2, chi, dev, dtype, seed=1)          # canonicalised on the GPU
+                torch.cuda.synchronize()
+                t_init = time.perf_counter() - t0
+                sw = qsb.Sweeps(1)
+                sw.set_schedule(maxdim=[chi], cutoff=[0.0], krylov_dim=[4], noise=[0.0])
+                key = "heis_f64_L100" if dtype == torch.float64 else "heis_c128_L100"
+                dm = qsb.DMRG(mps, [m.to(dev) for m in load_mpo(key, dtype)], device=dev, dtype=dtype)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                Es, _ = dm(sw, dispon=0, maxit=2)
+                torch.cuda.synchronize()
+                t_sweep = time.perf_counter() - t0
+            bd = dm.history["bond_dims"]
+            out["sweep"] = {"seconds": t_sweep, "bond_updates": len(Es), "updates_at_full_chi": int(sum(b == chi for b in bd)),
+                            "mps_init_on_gpu_s": t_init, "energy_end_of_sweep": float(Es[-1]),
+                            "peak_memory_gb": torch.cuda.max_memory_allocated() / 1e9,
+                            "what": f"one full two-site DMRG sweep, Heisenberg L={Lsites}, chi={chi}, {args.dtype}, "
+                                    "krylov_dim=4, maxit=2, cutoff=0, random right-canonical start; wall clock with a "
+                                    "device synchronise on both sides"}
+            del dm, mps
+            qsb.clear_workspaces()
+            torch.cuda.empty_cache()
+        except Exception as ex:
+            out["sweep"] = {"error": repr(ex)[:200]}
     # (4) CPU baseline: the oracle on the host cores, bounded sample of the same workload
     cores = os.cpu_count() or 1
     try:
