@@ -9,7 +9,11 @@ MPO bond W=5, d=2.  A *step* is one H_eff matvec  out = L . M1 . M2 . R . theta 
 quantum_simulation/dmrg.py:178-228, the operator Lanczos applies 8x per bond update).
 
   value        whole-job matvec throughput in GFLOP/s with every input resident in HBM, counted with the dense
-               ncon-order flop count the reference executes (qsb_heff_flops)
+               ncon-order flop count the reference executes (qsb_heff_flops) -- an EFFECTIVE rate: the
+               environments are in the canonical gauge a DMRG sweep produces (one identity channel in L and in R for a
+               finite-state-machine MPO), and the kernels skip the GEMM slices of those channels; ``executed`` carries
+               the flops actually executed, and the roofline / utilisation numbers are computed from THOSE
+               (``--dense-env`` benchmarks fully random environments instead: nothing to skip)
   e2e          the same metric through the reference-facing call ``ApplyMPO.forward`` with theta AND the result in
                pinned HOST memory: upload of theta + matvec + download of the result inside the timed region (the
                call pipelines them: column-block upload gating the step-1 GEMM, row-block download overlapped);
@@ -43,7 +47,6 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-NCU_TRAFFIC_STEP1_BYTES = 1.856138e9 + 675.188224e6     # ncu --set full, round 1, chi=2048 f64 step-1 GEMM
 METRIC = "H_eff matvec GFLOP/s (two-site DMRG bulk bond; default BASELINE config 3: Heisenberg L=100, chi=2048)"
 UNIT = "GFLOP/s"
 
@@ -60,6 +63,8 @@ def parse():
                     help="which BASELINE config's MPO bond to run (default: config 3, the headline)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "fused", "nccl"],
                     help="N>1: how theta shards are exchanged (auto = fused P2P push if available, else NCCL)")
+    ap.add_argument("--dense-env", action="store_true",
+                    help="fully random L and R (no identity channels): the round-1 workload, nothing is skipped")
     ap.add_argument("--no-sweep", action="store_true", help="skip the measured full DMRG sweep of the extras leg")
     ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / lanczos / env / library legs")
     return ap.parse_args()
@@ -77,13 +82,43 @@ MODELS = {   # model -> (MPO key for f64, for c128, left site of the bond, descr
     "tfim": ("tfim_c128_L100_g0.5", "tfim_c128_L100_g0.5", 50, "BASELINE config 2: transverse-field Ising chain L=100"),
 }
 _MODEL = "heis"
+_DENSE_ENV = False
+
+
+def fsm_identity_channels(mpo, site):
+    """Which channel of L[site] and of R[site+2] is the identity for a canonical MPS?  Structural propagation through
+    the MPO chain (the reference's FSM layout, mpo/auto_mpo/finite_state_machine.py:662-700): the boundary
+    environments are ones(W,1,1) (dmrg.py:349-351); channel w' of L[p+1] is A^H A = 1 iff column w' of M[p] holds a
+    single non-zero block, that block is the d x d identity, and it comes from an identity channel of L[p].  Mirror
+    image from the right.  Returns (idL, idR), -1 where there is none.  (tests/test_gpu_contract.py checks the same
+    channels NUMERICALLY on environments built from a canonical MPS.)"""
+    def step(M, ids, left):
+        Wi, Wo = (M.shape[0], M.shape[1]) if left else (M.shape[1], M.shape[0])
+        blk = (lambda i, o: M[i, o]) if left else (lambda i, o: M[o, i])
+        eye = torch.eye(M.shape[2], dtype=M.dtype)
+        out = set()
+        for o in range(Wo):
+            src = [i for i in range(Wi) if bool((blk(i, o) != 0).any())]
+            if len(src) == 1 and src[0] in ids and torch.equal(blk(src[0], o), eye):
+                out.add(o)
+        return out
+    idsL = set(range(mpo[0].shape[0])) if mpo[0].shape[0] == 1 else set()
+    for p in range(site):
+        idsL = step(mpo[p].cpu(), idsL, True)
+    idsR = set(range(mpo[-1].shape[1])) if mpo[-1].shape[1] == 1 else set()
+    for p in range(len(mpo) - 1, site + 1, -1):
+        idsR = step(mpo[p].cpu(), idsR, False)
+    return (min(idsL) if idsL else -1), (min(idsR) if idsR else -1)
 
 
 def make_inputs(chi, dtype, device, rows=None, row0=0):
     """Seeded synthetic bulk-bond inputs: real MPO site tensors of the model, random L/R/theta.
-    Generated per row so that any row shard sees exactly the rows of the global problem."""
+    Generated per row so that any row shard sees exactly the rows of the global problem.  Unless --dense-env, the
+    environments are in the gauge a sweep produces: the FSM's "nothing yet" channel of L and "all done" channel of R
+    are identity matrices (A^H A = 1 for a canonical MPS); every other channel is dense random."""
     kf, kc, site, _ = MODELS[_MODEL]
     mpo = load_mpo(kf if dtype == torch.float64 else kc, dtype)
+    idL, idR = (-1, -1) if _DENSE_ENV else fsm_identity_channels(mpo, site)
     M1, M2 = mpo[site].to(device), mpo[site + 1].to(device)
     W = M1.shape[0]
     g = torch.Generator(device="cpu").manual_seed(0)
@@ -95,7 +130,25 @@ def make_inputs(chi, dtype, device, rows=None, row0=0):
     gt = torch.Generator(device=device).manual_seed(2)
     theta = torch.randn(chi * M1.shape[3] * M2.shape[3] * chi, dtype=dtype, device=device, generator=gt)
     theta /= torch.linalg.norm(theta)
+    if idL >= 0:
+        L[idL].zero_()
+        r = torch.arange(rows, device=device)
+        L[idL, r, r + row0] = 1.0
+    if idR >= 0:
+        R[idR] = torch.eye(chi, dtype=dtype, device=device)
     return L, M1, M2, R, theta
+
+
+def hermitian_envs(L, R):
+    """Hermitian versions of square environments for the Lanczos legs, identity channels kept as they are."""
+    def herm(env):
+        eye = torch.eye(env.shape[1], dtype=env.dtype, device=env.device)
+        out = env + env.conj().transpose(1, 2)
+        for w in range(env.shape[0]):
+            if torch.equal(env[w], eye):
+                out[w] = eye
+        return out
+    return herm(L), herm(R)
 
 
 class ClockSampler:
@@ -195,7 +248,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": workload_config(args, 1),
+            "config": workload_config(args, args.gpus),
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -210,6 +263,8 @@ def workload_config(args, world):
                         f"{M1.shape[0]}-{M1.shape[1]}-{M2.shape[1]}, d={M1.shape[2]}, "
                         f"{'float64' if args.dtype == 'f64' else 'complex128'}; one H_eff matvec per step",
             "chi": args.chi, "d": int(M1.shape[2]), "W": int(M1.shape[0]), "hamiltonian": args.model,
+            "environments": ("dense random" if args.dense_env else
+                             "canonical gauge: identity channel in L and R (as a sweep produces), other channels dense random"),
             "parallelism": "single GPU" if world == 1 else f"left-bond row shards x{world}",
             "l2_policy": "inputs + intermediates per step (>1 GB at chi=2048) exceed the 126 MB L2; no flush needed"}
 
@@ -217,6 +272,20 @@ def workload_config(args, world):
 # ----------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------
+def measured_traffic(args, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed ncu
+    --set full capture of this round (profiles/r02_ncu_traffic.json, written by tools/ncu_summary.py from the .ncu-rep);
+    None when no capture matches this configuration."""
+    path = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
+    key = f"{args.model}/chi{args.chi}/{args.dtype}/n{world}/{'dense' if args.dense_env else 'canonical'}"
+    try:
+        z = json.load(open(path))
+        e = z[key]
+        return float(e["dram_bytes"]), f"{path.replace(ROOT + os.sep, '')}[{key}]: {e.get('source', '')}"
+    except Exception:
+        return None, f"no ncu capture committed for {key}"
+
+
 def time_region(fn, steps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
@@ -243,11 +312,17 @@ def run_ours(args):
     assert chi % world == 0
     rows = chi // world
     L, M1, M2, R, theta = make_inputs(chi, dtype, dev, rows=rows, row0=rank * rows)
+    # what EnvironmentManager does after every environment update: test the channels for the identity (one small
+    # kernel + a W-double read-back) and remember the answer on the tensor; ApplyMPO.forward picks it up
+    _lib.tag_identity(L, rank * rows)
+    _lib.tag_identity(R)
+    ident = (_lib.identity_of(L)[0], _lib.identity_of(R)[0], rank * rows)
     n = theta.numel()
     n_loc = rows * M1.shape[2] * M2.shape[2] * chi
     op = qsb.ApplyMPO("ncon")
     out = torch.empty(n_loc, dtype=dtype, device=dev)
-    flops_local = _lib.heff_flops(theta, L, M1, M2, R)
+    flops_local = _lib.heff_flops(theta, L, M1, M2, R)                       # dense ncon-order count ("effective")
+    flops_exec_local = _lib.heff_flops_executed(theta, L, M1, M2, R, ident)  # what the kernels execute
     flops_total = flops_local * world
 
     theta_shard = theta.view(world, -1)[rank].clone() if world > 1 else None
@@ -319,22 +394,23 @@ def run_ours(args):
     g4 = [evs[i][2].elapsed_time(evs[i][3]) for i in range(K)]
     c = 8.0 if dtype.is_complex else 2.0
     W, d2 = M1.shape[0], M1.shape[3] * M2.shape[3]
-    g1_flops = c * W * rows * chi * d2 * chi            # step-1 GEMM: algorithmic flops per launch
-    g4_flops = c * chi * (M2.shape[1] * chi) * (M1.shape[2] * M2.shape[2] * rows)
+    Wl_exec = W - (1 if ident[0] >= 0 else 0)           # GEMM slices actually executed (identity channels skipped)
+    Wr_exec = M2.shape[1] - (1 if ident[1] >= 0 else 0)
+    g1_flops = c * Wl_exec * rows * chi * d2 * chi      # step-1 GEMM: flops EXECUTED per launch (one launch per step)
+    g4_flops = c * chi * (Wr_exec * chi) * (M1.shape[2] * M2.shape[2] * rows)
     g1_ms = sum(g1) / K
     achieved = g1_flops / (g1_ms * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "gemm (FP64 DMMA), H_eff step 1", "achieved": achieved,
+    traffic, traffic_src = measured_traffic(args, world)
+    roofline = {"bound": "tensor", "kernel": "gemm_tma_kernel (FP64 DMMA), H_eff step 1", "achieved": achieved,
                 "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
-                "traffic": NCU_TRAFFIC_STEP1_BYTES if (chi == 2048 and world == 1 and dtype == torch.float64) else None,
-                "traffic_source": "profiles/r01_gemm_tma_streamk_ncu_full.md (dram__bytes_read.sum + "
-                                  "dram__bytes_write.sum of one launch; algorithmic 0.97 GB; DRAM at 3-5 % of peak, "
-                                  "the kernel is tensor-bound)",
+                "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": "measured in this run: register-resident mma.sync.m8n8k4.f64 issue-rate probe "
                                "(qsb_probe_dmma); MEASURED_PEAKS.json has no FP64 entry",
                 "algorithmic_flops_per_launch": g1_flops, "avg_launch_ms": g1_ms,
+                "channels_executed": {"step1": Wl_exec, "of": W, "step4": Wr_exec, "of_r": int(M2.shape[1])},
                 "stage_ms": {"gemm_step1": g1_ms, "mpo_mix": sum(mix) / K, "gemm_step4": sum(g4) / K},
                 "step4_tflops": g4_flops / (sum(g4) / K * 1e-3) / 1e12,
-                "matvec_frac_of_peak": (flops_local / (ms_step * 1e-3) / 1e12) / peak_tf if peak_tf else None}
+                "matvec_frac_of_peak": (flops_exec_local / (ms_step * 1e-3) / 1e12) / peak_tf if peak_tf else None}
 
     # ---- e2e: the public call with the step's input in pinned HOST memory and the result read back to the host,
     # both copies inside the timed region.  N > 1: every rank uploads ITS shard of theta (the sharded operator's
@@ -385,15 +461,23 @@ def run_ours(args):
                     "quantum_simulation_b200.parallel.FusedShardedApplyMPO / ShardedApplyMPO")
                    + " (torch.ops.qsb200.heff_apply* -> qsb_heff_apply)"}
 
+    exec_tf = flops_exec_local * world / (sec / K) / 1e12
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": args.dtype, "data": "synthetic", "config": dict(workload_config(args, world), exchange=exchange),
+            "dtype": args.dtype, "data": "synthetic", "config": workload_config(args, world), "exchange": exchange,
             "clocks": clocks,
             "e2e": e2e, "gpu_launches": launches["total"], "launch_breakdown": launches, "roofline": roofline,
-            "tflops": value / 1e3, "frac_of_fp64_tensor_peak": (value / 1e3 / world) / peak_tf if peak_tf else None}
+            "tflops": value / 1e3,
+            "executed": {"tflops": exec_tf, "flops_per_step": flops_exec_local * world,
+                         "dense_flops_per_step": flops_total, "identity_channels": {"L": ident[0], "R": ident[1]},
+                         "note": "value counts the dense ncon-order flops the reference executes (effective rate); "
+                                 "this is what the kernels execute -- utilisation numbers use it"},
+            "frac_of_fp64_tensor_peak": (exec_tf / world) / peak_tf if peak_tf else None}
 
     if rank == 0 and world == 1 and not args.no_extras:
         line.update(extras(args, qsb, _lib, dev, dtype, L, M1, M2, R, theta, peak_tf))
+        if line.get("cublas_dgemm_8192_tflops"):
+            line["roofline_frac_vs_cublas_dgemm"] = roofline["achieved"] / line["cublas_dgemm_8192_tflops"]
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
@@ -415,6 +499,7 @@ def extras(args, qsb, _lib, dev, dtype, L, M1, M2, R, theta, peak_tf):
             torch.matmul(a, b)
         s = time_region(lambda: torch.matmul(a, b), 5) / 5
         out["cublas_dgemm_8192_tflops"] = 2 * 8192 ** 3 / s / 1e12
+        out["roofline_frac_vs_cublas_dgemm"] = None         # filled by the caller from roofline.achieved
         del a, b
         for _ in range(2):
             orc.apply_mpo(theta, L, M1, M2, R)
@@ -434,7 +519,9 @@ def extras(args, qsb, _lib, dev, dtype, L, M1, M2, R, theta, peak_tf):
     # (2) Lanczos: one full solve (2 restarts x krylov 4 = 8 matvecs + fused vector ops), vector-op bandwidth
     n = theta.numel()
     op = qsb.ApplyMPO()
-    args_op = (L, M1, M2, R)
+    Lh, Rh = hermitian_envs(L, R)
+    _lib.tag_identity(Lh), _lib.tag_identity(Rh)
+    args_op = (Lh, M1, M2, Rh)
     qsb.lanczos_ground_state(theta, op, args_op, num_restarts=2, krylov_dim=4)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -478,8 +565,7 @@ def extras(args, qsb, _lib, dev, dtype, L, M1, M2, R, theta, peak_tf):
     try:
         from quantum_simulation_b200.svd import two_site_split
         d = M1.shape[2]
-        Ls = Lsq + Lsq.conj().transpose(1, 2)
-        Rs = R + R.conj().transpose(1, 2)
+        Ls, Rs = Lh, Rh
         A = torch.randn(chi, d, chi, dtype=dtype, device=dev) / chi ** 0.5
 
         def timed(fn, reps=2):
@@ -529,7 +615,7 @@ def extras(args, qsb, _lib, dev, dtype, L, M1, M2, R, theta, peak_tf):
             import contextlib
             import io
             Lsites = 100
-            del L, R, theta
+            del L, R, theta, Lh, Rh, args_op
             _lib.release_workspaces()
             qsb.clear_workspaces()
             torch.cuda.empty_cache()
@@ -576,8 +662,10 @@ def extras(args, qsb, _lib, dev, dtype, L, M1, M2, R, theta, peak_tf):
 
 def main():
     global _MODEL
+    global _DENSE_ENV
     args = parse()
     _MODEL = args.model
+    _DENSE_ENV = args.dense_env
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -90,12 +90,30 @@ typedef struct {
     int chunk_local;        /* 1: block chunk_rot is already in place (stream-ordered before this call), do not gate it.
                                Required when that block is copied on the SAME device: such a copy may need SMs, which the
                                persistent GEMM would be holding while it waits for the flag. */
+    /* Identity-channel shortcut (MPO-sparsity-aware block skipping in the chi^3 GEMMs).  For finite-state-machine
+       MPOs (mpo/auto_mpo/finite_state_machine.py:662-700) the "nothing has happened yet" channel of the left
+       environment and the "everything is done" channel of the right one are identity matrices whenever the MPS is in
+       canonical form (boundary ones(W,1,1), dmrg.py:349-351, times isometries).  The caller VERIFIES this numerically
+       (qsb_env_identity_deviation) and passes 1 + the channel index (0 = no such channel).  Step 1 then skips the GEMM
+       with L[w] (T1[w] is theta itself), step 4 skips the panel of R[w] (its T3 slice goes straight to `out`).
+       Requires chi_l_out <= chi_l_in resp. chi_r_out == chi_r_in; ignored otherwise. */
+    int L_identity;         /* 1 + w with L[w][a'][a] == delta(a, a' + L_row0) */
+    int R_identity;         /* 1 + w with R[w][b'][b] == delta(b, b') */
+    int L_row0;             /* first row of the bra index held by a row-sharded L (multi-GPU), else 0 */
 } qsb_heff_desc;
 
 int qsb_heff_workspace_bytes(const qsb_heff_desc* d, size_t* bytes);
 int qsb_heff_apply(const qsb_heff_desc* d, void* stream);
-/* dense ncon-order flop count of one matvec; what the roofline uses */
+/* dense ncon-order flop count of one matvec: the "effective" figure */
 double qsb_heff_flops(const qsb_heff_desc* d);
+/* flops the two GEMMs of THIS call execute (identity channels skipped) plus the dense mix count: the figure a
+   tensor-pipe utilisation must be computed from (never credit skipped work) */
+double qsb_heff_flops_executed(const qsb_heff_desc* d);
+/* maxdev[w] = max over (r, c) of | env[w][r][c] - delta(c, r + row0) |  for every channel w < W of an environment
+   (W, rows, cols) with element strides: the numerical test behind L_identity / R_identity.  maxdev: W doubles on the
+   device, written stream-ordered. */
+int qsb_env_identity_deviation(int dtype, int W, int rows, int cols, const void* env, const int64_t stride[3],
+                               int row0, double* maxdev, void* stream);
 /* Profiling hook: with count == 4 every following qsb_heff_apply records these cudaEvent_t on its stream:
    [0] before step 1, [1] after step 1 (GEMM), [2] after the MPO mix, [3] after step 4 (GEMM).
    count == 0 clears the hook.  Used by bench.py to time the dominant kernel inside the timed region. */
@@ -136,6 +154,9 @@ typedef struct {
        right: site_bra = B[lo:lo+chi_bra] -> out holds rows [lo, lo+chi_bra) of the new environment. */
     int chi_bra;
     const void* site_bra; int64_t site_bra_stride[3];
+    /* 1 + w of an identity channel of `env` (verified by the caller, see qsb_heff_desc.L_identity): the first GEMM
+       with that slice is replaced by a (conjugating) copy of the site tensor.  Plain form only (chi_bra == 0). */
+    int env_identity;
 } qsb_env_desc;
 
 int qsb_env_workspace_bytes(const qsb_env_desc* d, size_t* bytes);
@@ -191,8 +212,14 @@ typedef struct {
     const void* B; int64_t b_ns, b_ks, b_ps, b_zs; int conjB;
     void*       C; int64_t c_ms, c_ns, c_zs;
     int force_path;         /* 0 = auto, 1 = TMA (error if not eligible), 2 = cp.async */
+    int accumulate;         /* 1: C += A.B */
 } qsb_gemm_desc;
 int qsb_gemm(const qsb_gemm_desc* g, void* stream);
+
+/* sizeof of the descriptor structs as this library was compiled: a binding asserts them against its own mirror */
+size_t qsb_sizeof_heff_desc(void);
+size_t qsb_sizeof_env_desc(void);
+size_t qsb_sizeof_gemm_desc(void);
 
 /* Register-resident DMMA issue-rate probe: runs `iters` rounds of independent
    mma.sync.m8n8k4.f64 on every SM and returns the flops issued in *flops.

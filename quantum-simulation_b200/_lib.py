@@ -32,6 +32,8 @@ EXPORTS = [
     "qsb_env_workspace_bytes", "qsb_env_left", "qsb_env_right", "qsb_env_flops",
     "qsb_lz_scratch_bytes", "qsb_lz_dot", "qsb_lz_axpy_norm", "qsb_lz_scale", "qsb_lz_combine",
     "qsb_strided_copy3", "qsb_gemm", "qsb_probe_dmma", "qsb_push_shard", "qsb_push_shard_dma", "qsb_upload_columns",
+    "qsb_heff_flops_executed", "qsb_env_identity_deviation",
+    "qsb_sizeof_heff_desc", "qsb_sizeof_env_desc", "qsb_sizeof_gemm_desc",
 ]
 
 
@@ -51,6 +53,7 @@ class HeffDesc(C.Structure):
         ("chunk_flags", C.c_void_p),
         ("chunk_axis", C.c_int),
         ("chunk_local", C.c_int),
+        ("L_identity", C.c_int), ("R_identity", C.c_int), ("L_row0", C.c_int),
     ]
 
 
@@ -65,6 +68,7 @@ class EnvDesc(C.Structure):
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
         ("chi_bra", C.c_int),
         ("site_bra", C.c_void_p), ("site_bra_stride", C.c_int64 * 3),
+        ("env_identity", C.c_int),
     ]
 
 
@@ -78,6 +82,7 @@ class GemmDesc(C.Structure):
         ("conjB", C.c_int),
         ("C", C.c_void_p), ("c_ms", C.c_int64), ("c_ns", C.c_int64), ("c_zs", C.c_int64),
         ("force_path", C.c_int),
+        ("accumulate", C.c_int),
     ]
 
 
@@ -123,6 +128,15 @@ def load() -> C.CDLL:
     lib.qsb_upload_columns.argtypes = [vp, vp, i64, i64, i32, i32, vp, i32, vp]
     lib.qsb_push_shard_dma.argtypes = [vp, C.c_size_t, C.POINTER(vp), C.POINTER(vp), i32, i32, vp]
     lib.qsb_probe_dmma.argtypes = [i32, C.POINTER(C.c_double), vp, vp]
+    lib.qsb_heff_flops_executed.argtypes = [C.POINTER(HeffDesc)]
+    lib.qsb_heff_flops_executed.restype = C.c_double
+    lib.qsb_env_identity_deviation.argtypes = [i32, i32, i32, i32, vp, C.POINTER(i64), i32, vp, vp]
+    for fn, st in (("qsb_sizeof_heff_desc", HeffDesc), ("qsb_sizeof_env_desc", EnvDesc),
+                   ("qsb_sizeof_gemm_desc", GemmDesc)):
+        getattr(lib, fn).restype = C.c_size_t
+        if getattr(lib, fn)() != C.sizeof(st):          # a stale .so or a drifted mirror must not run
+            raise RuntimeError(f"qsb200: {fn}() = {getattr(lib, fn)()} but the ctypes mirror has {C.sizeof(st)} bytes; "
+                               "rebuild lib/libqsb200.so")
     for name in EXPORTS:          # every symbol include/qsb200.h declares must be exported
         getattr(lib, name)
     _lib = lib
@@ -208,8 +222,53 @@ def release_workspaces() -> None:
 # ---------------------------------------------------------------------------------------------
 # descriptors
 # ---------------------------------------------------------------------------------------------
+IDENTITY_TOL = 1e-13      # max |env[w] - 1| below which a channel counts as the identity; 0 disables the shortcut
+_IDENT_ATTR = "_qsb_identity"
+
+
+def identity_channel(env: torch.Tensor, row0: int = 0, tol: Optional[float] = None) -> int:
+    """Index of the first channel w with env[w] == identity (rows shifted by ``row0`` for a row shard) to within
+    ``tol`` in the max norm, or -1.  One small kernel + one host read-back of W doubles."""
+    tol = IDENTITY_TOL if tol is None else tol
+    if tol <= 0 or env.dim() != 3 or env.shape[1] > env.shape[2] or env.dtype not in (torch.float64, torch.complex128):
+        return -1
+    dev = _require_cuda(env)
+    env = _resolved(env)
+    W, rows, cols = env.shape
+    dev_out = torch.empty(W, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        check(load().qsb_env_identity_deviation(dtype_code(env.dtype), W, rows, cols, env.data_ptr(),
+                                                (C.c_int64 * 3)(*env.stride()), int(row0), dev_out.data_ptr(),
+                                                _stream()), "identity_channel")
+    hit = torch.nonzero(dev_out.cpu() <= tol)
+    return int(hit[0]) if hit.numel() else -1
+
+
+def tag_identity(env: torch.Tensor, row0: int = 0) -> torch.Tensor:
+    """Test ``env`` for an identity channel and remember the answer ON the tensor object (the reference's call
+    signature ``ApplyMPO.forward(psi, L, M1, M2, R)`` has no room for it); returns ``env``."""
+    setattr(env, _IDENT_ATTR, (identity_channel(env, row0), int(row0), _version_of(env)))
+    return env
+
+
+def _version_of(t: torch.Tensor) -> int:
+    try:
+        return int(t._version)
+    except RuntimeError:            # inference tensors do not track versions
+        return -1
+
+
+def identity_of(env: torch.Tensor):
+    """(channel or -1, row0) recorded by ``tag_identity``; untagged tensors, and tensors written in place since
+    they were tagged, have no shortcut."""
+    tag = getattr(env, _IDENT_ATTR, None)
+    if tag is None or tag[2] != _version_of(env):
+        return (-1, 0)
+    return tag[:2]
+
+
 def heff_desc(psi: torch.Tensor, L: torch.Tensor, M1: torch.Tensor, M2: torch.Tensor, R: torch.Tensor,
-              out: Optional[torch.Tensor]) -> HeffDesc:
+              out: Optional[torch.Tensor], ident=(-1, -1, 0)) -> HeffDesc:
     if L.dim() != 3 or R.dim() != 3 or M1.dim() != 4 or M2.dim() != 4:
         raise AssertionError("[ApplyMPO] expected L,R rank 3 and M1,M2 rank 4")
     d = HeffDesc()
@@ -230,6 +289,7 @@ def heff_desc(psi: torch.Tensor, L: torch.Tensor, M1: torch.Tensor, M2: torch.Te
     d.R = R.data_ptr()
     d.R_stride = (C.c_int64 * 3)(*R.stride())
     d.out = out.data_ptr() if out is not None else None
+    d.L_identity, d.R_identity, d.L_row0 = ident[0] + 1, ident[1] + 1, ident[2]
     return d
 
 
@@ -237,10 +297,15 @@ def heff_flops(psi, L, M1, M2, R) -> float:
     return float(load().qsb_heff_flops(C.byref(heff_desc(psi, L, M1, M2, R, None))))
 
 
-def _impl_heff_apply(psi, L, M1, M2, R, out, gate=None) -> None:
+def heff_flops_executed(psi, L, M1, M2, R, ident=(-1, -1, 0)) -> float:
+    """Flops the kernels execute for this matvec (identity channels skipped) -- the utilisation numerator."""
+    return float(load().qsb_heff_flops_executed(C.byref(heff_desc(psi, L, M1, M2, R, None, ident))))
+
+
+def _impl_heff_apply(psi, L, M1, M2, R, out, gate=None, ident=(-1, -1, 0)) -> None:
     lib = load()
     dev = _require_cuda(psi, L, M1, M2, R, out)
-    d = heff_desc(psi, L, M1, M2, R, out)
+    d = heff_desc(psi, L, M1, M2, R, out, ident)
     if gate is not None:                   # (flags tensor, n_chunks, rot, epoch): fused all-gather -> matvec
         flags, d.n_chunks, d.chunk_rot, d.chunk_epoch, d.chunk_local = gate[:5]
         d.chunk_axis = gate[5] if len(gate) > 5 else 0
@@ -254,12 +319,20 @@ def _impl_heff_apply(psi, L, M1, M2, R, out, gate=None) -> None:
         check(lib.qsb_heff_apply(C.byref(d), _stream()), "ApplyMPO")
 
 
-def _impl_heff_apply_gated(psi, L, M1, M2, R, out, flags, n_chunks: int, rot: int, epoch: int, local: int) -> None:
-    _impl_heff_apply(psi, L, M1, M2, R, out, gate=(flags, n_chunks, rot, epoch, local))
+def _impl_heff_apply_ident(psi, L, M1, M2, R, out, l_ident: int, r_ident: int, l_row0: int) -> None:
+    _impl_heff_apply(psi, L, M1, M2, R, out, ident=(l_ident, r_ident, l_row0))
 
 
-def _impl_heff_apply_colgated(psi, L, M1, M2, R, out, flags, n_chunks: int, epoch: int) -> None:
-    _impl_heff_apply(psi, L, M1, M2, R, out, gate=(flags, n_chunks, 0, epoch, 0, 1))
+def _impl_heff_apply_gated(psi, L, M1, M2, R, out, flags, n_chunks: int, rot: int, epoch: int, local: int,
+                           l_ident: int = -1, r_ident: int = -1, l_row0: int = 0) -> None:
+    _impl_heff_apply(psi, L, M1, M2, R, out, gate=(flags, n_chunks, rot, epoch, local),
+                     ident=(l_ident, r_ident, l_row0))
+
+
+def _impl_heff_apply_colgated(psi, L, M1, M2, R, out, flags, n_chunks: int, epoch: int,
+                              l_ident: int = -1, r_ident: int = -1, l_row0: int = 0) -> None:
+    _impl_heff_apply(psi, L, M1, M2, R, out, gate=(flags, n_chunks, 0, epoch, 0, 1),
+                     ident=(l_ident, r_ident, l_row0))
 
 
 def upload_columns(src_host: torch.Tensor, dst: torch.Tensor, rows: int, row_elems: int, n_chunks: int,
@@ -301,7 +374,7 @@ def push_shard_dma(src: torch.Tensor, dst_ptrs: Sequence[int], flag_ptrs: Sequen
 
 
 def env_desc(env: torch.Tensor, M: torch.Tensor, site: torch.Tensor, out: Optional[torch.Tensor],
-             left: bool, site_bra: Optional[torch.Tensor] = None) -> EnvDesc:
+             left: bool, site_bra: Optional[torch.Tensor] = None, ident: int = -1) -> EnvDesc:
     if env.dim() != 3 or M.dim() != 4 or site.dim() != 3:
         raise AssertionError("[EnvUpdate] expected env rank 3, M rank 4, site tensor rank 3")
     d = EnvDesc()
@@ -337,6 +410,7 @@ def env_desc(env: torch.Tensor, M: torch.Tensor, site: torch.Tensor, out: Option
     d.site = site.data_ptr()
     d.site_stride = (C.c_int64 * 3)(*site.stride())
     d.out = out.data_ptr() if out is not None else None
+    d.env_identity = ident + 1 if site_bra is None else 0
     return d
 
 
@@ -344,10 +418,10 @@ def env_flops(env, M, site, left: bool) -> float:
     return float(load().qsb_env_flops(C.byref(env_desc(env, M, site, None, left))))
 
 
-def _impl_env(env, M, site, out, left: bool, site_bra=None) -> None:
+def _impl_env(env, M, site, out, left: bool, site_bra=None, ident: int = -1) -> None:
     lib = load()
     dev = _require_cuda(env, M, site, out)
-    d = env_desc(env, M, site, out, left, site_bra)
+    d = env_desc(env, M, site, out, left, site_bra, ident)
     nb = C.c_size_t(0)
     check(lib.qsb_env_workspace_bytes(C.byref(d), C.byref(nb)), "EnvUpdate")
     ws = workspace(dev, nb.value)
@@ -358,12 +432,12 @@ def _impl_env(env, M, site, out, left: bool, site_bra=None) -> None:
               "LeftEnvUpdate" if left else "RightEnvUpdate")
 
 
-def _impl_env_left(env, M, site, out) -> None:
-    _impl_env(env, M, site, out, True)
+def _impl_env_left(env, M, site, out, ident: int = -1) -> None:
+    _impl_env(env, M, site, out, True, ident=ident)
 
 
-def _impl_env_right(env, M, site, out) -> None:
-    _impl_env(env, M, site, out, False)
+def _impl_env_right(env, M, site, out, ident: int = -1) -> None:
+    _impl_env(env, M, site, out, False, ident=ident)
 
 
 def _impl_env_left_rows(env, M, site, site_bra, out) -> None:
@@ -424,7 +498,7 @@ def lz_scratch_bytes() -> int:
 # plain GEMM (tests, peak probe)
 # ---------------------------------------------------------------------------------------------
 def gemm(A: torch.Tensor, B: torch.Tensor, *, conjA: bool = False, conjB: bool = False,
-         force_path: int = 0) -> torch.Tensor:
+         force_path: int = 0, out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
     """C[z] = opA(A[z]) @ opB(B[z]) on the library's FP64 tensor-core core.  A: (Z, M, K) or (M, K);
     B: (Z, K, N) or (K, N); any strides with one unit stride per matrix."""
     lib = load()
@@ -435,7 +509,14 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, conjA: bool = False, conjB: bool =
     Z, M, K = A.shape
     Zb, Kb, N = B.shape
     assert Kb == K and Zb in (1, Z)
-    out = torch.empty(Z, M, N, dtype=A.dtype, device=dev)
+    if out is None:
+        if accumulate:
+            raise ValueError("gemm: accumulate=True needs `out`")
+        out = torch.empty(Z, M, N, dtype=A.dtype, device=dev)
+    else:
+        out = out.unsqueeze(0) if squeeze else out
+        if tuple(out.shape) != (Z, M, N) or not out.is_contiguous() or out.dtype != A.dtype:
+            raise ValueError("gemm: `out` must be a contiguous (Z, M, N) tensor of the operands' dtype")
     g = GemmDesc()
     g.dtype = dtype_code(A.dtype)
     g.M, g.N, g.K, g.P, g.Z = M, N, K, 1, Z
@@ -444,6 +525,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, conjA: bool = False, conjB: bool =
                                                    B.stride(2), 0, int(conjB))
     g.C, g.c_zs, g.c_ms, g.c_ns = out.data_ptr(), M * N, N, 1
     g.force_path = force_path
+    g.accumulate = int(accumulate)
     with torch.cuda.device(dev):
         check(lib.qsb_gemm(C.byref(g), _stream()), "gemm")
     return out[0] if squeeze else out
@@ -478,13 +560,15 @@ def register_ops() -> None:
         return
     tl = torch.library.Library("qsb200", "DEF")
     tl.define("heff_apply(Tensor psi, Tensor L, Tensor M1, Tensor M2, Tensor R, Tensor(a!) out) -> ()")
+    tl.define("heff_apply_ident(Tensor psi, Tensor L, Tensor M1, Tensor M2, Tensor R, Tensor(a!) out, int l_ident, "
+              "int r_ident, int l_row0) -> ()")
     tl.define("heff_apply_gated(Tensor psi, Tensor L, Tensor M1, Tensor M2, Tensor R, Tensor(a!) out, Tensor flags, "
-              "int n_chunks, int rot, int epoch, int local) -> ()")
+              "int n_chunks, int rot, int epoch, int local, int l_ident=-1, int r_ident=-1, int l_row0=0) -> ()")
     tl.define("heff_apply_colgated(Tensor psi, Tensor L, Tensor M1, Tensor M2, Tensor R, Tensor(a!) out, Tensor flags, "
-              "int n_chunks, int epoch) -> ()")
+              "int n_chunks, int epoch, int l_ident=-1, int r_ident=-1, int l_row0=0) -> ()")
     tl.define("push_shard(Tensor src, int[] dst_ptrs, int[] flag_ptrs, int epoch, Tensor(a!) ticket) -> ()")
-    tl.define("env_left(Tensor env, Tensor M, Tensor site, Tensor(a!) out) -> ()")
-    tl.define("env_right(Tensor env, Tensor M, Tensor site, Tensor(a!) out) -> ()")
+    tl.define("env_left(Tensor env, Tensor M, Tensor site, Tensor(a!) out, int ident=-1) -> ()")
+    tl.define("env_right(Tensor env, Tensor M, Tensor site, Tensor(a!) out, int ident=-1) -> ()")
     tl.define("env_left_rows(Tensor env, Tensor M, Tensor site, Tensor site_bra, Tensor(a!) out) -> ()")
     tl.define("env_right_rows(Tensor env, Tensor M, Tensor site, Tensor site_bra, Tensor(a!) out) -> ()")
     tl.define("lz_dot(Tensor X, int m, int ldx, Tensor w, int n, Tensor(a!) scal, int out_idx, int flags, "
@@ -495,6 +579,7 @@ def register_ops() -> None:
     tl.define("lz_combine(Tensor X, int m, int ldx, float[] y, Tensor(a!) dst, int n, Tensor(b!) scal, "
               "int norm_idx, int flags, Tensor(c!) scratch) -> ()")
     tl.impl("heff_apply", _impl_heff_apply, "CUDA")
+    tl.impl("heff_apply_ident", _impl_heff_apply_ident, "CUDA")
     tl.impl("heff_apply_gated", _impl_heff_apply_gated, "CUDA")
     tl.impl("heff_apply_colgated", _impl_heff_apply_colgated, "CUDA")
     tl.impl("push_shard", _impl_push_shard, "CUDA")

@@ -37,6 +37,7 @@ struct GemmArgs {
     int ksplit = 1, krot = 0, kepoch = 0, klocal = 0;
     int nsplit = 1;                 // > 1: gate whole tiles on the arrival of their COLUMN block of B
     const int* kflags = nullptr;
+    int accumulate = 0;             // 1: C += A.B (C must hold valid data), 0: C = A.B
 };
 int gemm_launch(const GemmArgs& g, cudaStream_t stream);
 

@@ -38,6 +38,9 @@ struct PrepArgs {
     long long m_ro, m_ri, m_co, m_ci;
     // input offsets of a column
     long long i_s0, i_s1;
+    // identity-channel shortcut: columns of outer index id_co read their input at id_delta + ci*i_s1 (relative to
+    // the mix input base) instead of co*i_s0 + ci*i_s1 -- i.e. from theta itself rather than from a T1 slab
+    int id_co = -1; long long id_delta = 0;
     PlanPtrs p;
 };
 
@@ -90,7 +93,7 @@ __global__ void __launch_bounds__(256) mix_prepare_kernel(const PrepArgs a) {
             const T v = G[(long long)r * a.C + c];
             if (nz(v)) {
                 const int co = c / a.CI, ci = c - co * a.CI;
-                a.p.colofs[q] = co * a.i_s0 + ci * a.i_s1;
+                a.p.colofs[q] = (co == a.id_co ? a.id_delta : co * a.i_s0) + ci * a.i_s1;
                 vals[q] = v;
                 ++q;
             }
@@ -107,6 +110,8 @@ struct MixArgs {
     int R, RI;
     long long o_s0, o_s1, i_us, o_us;
     int U, X;
+    // identity-channel shortcut: rows of outer index id_ro are written to out2 + u*o2_us + ri*o2_s1 + x
+    int id_ro = -1; char* out2 = nullptr; long long o2_us = 0, o2_s1 = 0;
 };
 
 template <bool CPLX, int VEC>      // VEC: x values per thread (2 = double2 path, real only)
@@ -117,6 +122,7 @@ __global__ void __launch_bounds__(256) mix_apply_kernel(const MixArgs a) {
         if constexpr (CPLX) {
             const double2* in = reinterpret_cast<const double2*>(a.in) + (long long)u * a.i_us + x;
             double2* out = reinterpret_cast<double2*>(a.out) + (long long)u * a.o_us + x;
+            double2* out2 = reinterpret_cast<double2*>(a.out2) + (long long)u * a.o2_us + x;
             const double2* vals = reinterpret_cast<const double2*>(a.vals);
             for (int r = 0; r < a.R; ++r) {
                 double re = 0.0, im = 0.0;
@@ -128,11 +134,13 @@ __global__ void __launch_bounds__(256) mix_apply_kernel(const MixArgs a) {
                     im += v.x * t.y + v.y * t.x;
                 }
                 const int ro = r / a.RI, ri = r - ro * a.RI;
-                out[ro * a.o_s0 + ri * a.o_s1] = make_double2(re, im);
+                if (ro == a.id_ro) out2[ri * a.o2_s1] = make_double2(re, im);
+                else out[ro * a.o_s0 + ri * a.o_s1] = make_double2(re, im);
             }
         } else if constexpr (VEC == 2) {
             const double* in = reinterpret_cast<const double*>(a.in) + (long long)u * a.i_us + x;
             double* out = reinterpret_cast<double*>(a.out) + (long long)u * a.o_us + x;
+            double* out2 = reinterpret_cast<double*>(a.out2) + (long long)u * a.o2_us + x;
             const double* vals = reinterpret_cast<const double*>(a.vals);
             for (int r = 0; r < a.R; ++r) {
                 double s0 = 0.0, s1 = 0.0;
@@ -143,18 +151,21 @@ __global__ void __launch_bounds__(256) mix_apply_kernel(const MixArgs a) {
                     s0 += v * t.x; s1 += v * t.y;
                 }
                 const int ro = r / a.RI, ri = r - ro * a.RI;
-                *reinterpret_cast<double2*>(out + ro * a.o_s0 + ri * a.o_s1) = make_double2(s0, s1);
+                double* dst = (ro == a.id_ro) ? out2 + ri * a.o2_s1 : out + ro * a.o_s0 + ri * a.o_s1;
+                *reinterpret_cast<double2*>(dst) = make_double2(s0, s1);
             }
         } else {
             const double* in = reinterpret_cast<const double*>(a.in) + (long long)u * a.i_us + x;
             double* out = reinterpret_cast<double*>(a.out) + (long long)u * a.o_us + x;
+            double* out2 = reinterpret_cast<double*>(a.out2) + (long long)u * a.o2_us + x;
             const double* vals = reinterpret_cast<const double*>(a.vals);
             for (int r = 0; r < a.R; ++r) {
                 double s0 = 0.0;
                 const int q1 = a.rowptr[r + 1];
                 for (int q = a.rowptr[r]; q < q1; ++q) s0 += vals[q] * __ldg(in + a.colofs[q]);
                 const int ro = r / a.RI, ri = r - ro * a.RI;
-                out[ro * a.o_s0 + ri * a.o_s1] = s0;
+                if (ro == a.id_ro) out2[ri * a.o2_s1] = s0;
+                else out[ro * a.o_s0 + ri * a.o_s1] = s0;
             }
         }
     }
@@ -190,7 +201,7 @@ static int launch_prepare(bool cplx, const PrepArgs& a, cudaStream_t s) {
     return check_launch();
 }
 
-static int launch_mix(bool cplx, const MixArgs& a, cudaStream_t s) {
+static int launch_mix(bool cplx, const MixArgs& a, cudaStream_t s, bool offsets_even = true) {
     if (a.U <= 0 || a.X <= 0 || a.R <= 0) return QSB_OK;
     const int gy = a.U < 65535 ? a.U : 65535;
     if (cplx) {
@@ -199,7 +210,8 @@ static int launch_mix(bool cplx, const MixArgs& a, cudaStream_t s) {
     } else {
         auto even = [](long long v) { return (v & 1) == 0; };
         const bool v2 = even(a.X) && even(a.i_us) && even(a.o_us) && even(a.o_s0) && even(a.o_s1) &&
-                        aligned16(a.in) && aligned16(a.out);
+                        aligned16(a.in) && aligned16(a.out) && offsets_even &&
+                        (a.id_ro < 0 || (even(a.o2_us) && even(a.o2_s1) && aligned16(a.out2)));
         // column offsets are multiples of X-sized rows: even whenever X and the slab strides are even,
         // which the callers guarantee together with v2 (offsets are built from the same extents)
         if (v2) {
@@ -363,6 +375,18 @@ extern "C" int qsb_heff_apply(const qsb_heff_desc* d, void* stream_) {
         R = ws + h.off_Rc; Rs[0] = cro * cri; Rs[1] = cri; Rs[2] = 1;
     }
 
+    // identity-channel shortcut (see qsb_heff_desc): which slices of L and R are (verified) identities
+    const long long es = cplx ? 16 : 8;
+    int idL = d->L_identity - 1, idR = d->R_identity - 1;
+    if (idL >= d->W_l || clo > cli || d->L_row0 < 0 || d->L_row0 + clo > cli) idL = -1;
+    if (idR >= d->W_r || cro != cri) idR = -1;
+    long long id_delta = 0;
+    if (idL >= 0) {      // T1[idL] is theta (rows L_row0 ..): the mix reads it in place, through an element offset
+        const long long diff = ((const char*)d->theta + (long long)d->L_row0 * N1 * es) - T1;
+        if (diff % es != 0) idL = -1; else id_delta = diff / es;
+    }
+    if (idL >= 0 && d->n_chunks > 1 && d->W_l == 1) idL = -1;     // gated upload: some GEMM must wait for the blocks
+
     // mix operator G = M1 . M2, rows (w_r, s1', s2'), columns (w_l, s1, s2)
     PrepArgs pa{};
     pa.mode = 0;
@@ -370,28 +394,37 @@ extern "C" int qsb_heff_apply(const qsb_heff_desc* d, void* stream_) {
     pa.M1 = (const char*)d->M1; pa.M2 = (const char*)d->M2;
     pa.W_m = d->W_m; pa.W_r = d->W_r; pa.d1o = d->d1_out; pa.d1i = d->d1_in; pa.d2o = d->d2_out; pa.d2i = d->d2_in;
     pa.i_s0 = clo * N1; pa.i_s1 = cri;
+    pa.id_co = idL; pa.id_delta = id_delta;
     pa.p = pp;
     if ((rc = launch_prepare(cplx, pa, stream))) return rc;
 
     // step 1 (label 1 of dmrg.py:218-221):  T1[w][a'][s1 s2 b] = sum_a L[w][a'][a] theta[a][s1 s2 b]
+    // one launch per run of consecutive non-identity channels (FSM MPOs: one run, w = 1 .. W_l-1)
     stage_mark(0, stream);
-    GemmArgs g1{};
-    g1.cplx = cplx; g1.M = (int)clo; g1.N = (int)N1; g1.K = (int)cli; g1.P = 1; g1.Z = d->W_l;
-    g1.A = L; g1.a_rs = Ls[1]; g1.a_ks = Ls[2]; g1.a_ps = 0; g1.a_zs = Ls[0]; g1.conjA = 0;
-    g1.B = d->theta; g1.b_rs = 1; g1.b_ks = N1; g1.b_ps = 0; g1.b_zs = 0; g1.conjB = 0;
-    g1.C = T1; g1.c_ms = N1; g1.c_ns = 1; g1.c_zs = clo * N1;
-    g1.force_path = 0;
-    if (d->n_chunks > 1) {           // fused all-gather -> GEMM: gate the k chunks on their arrival flags
-        if (!d->chunk_flags) return QSB_ERR_ARG;
-        g1.kepoch = d->chunk_epoch; g1.kflags = d->chunk_flags;
-        if (d->chunk_axis == 1) { g1.nsplit = d->n_chunks; }
-        else { g1.ksplit = d->n_chunks; g1.krot = d->chunk_rot; g1.klocal = d->chunk_local; }
-        g1.force_path = 1;
+    for (int w0 = 0; w0 < d->W_l;) {
+        if (w0 == idL) { ++w0; continue; }
+        int w1 = w0;
+        while (w1 < d->W_l && w1 != idL) ++w1;
+        GemmArgs g1{};
+        g1.cplx = cplx; g1.M = (int)clo; g1.N = (int)N1; g1.K = (int)cli; g1.P = 1; g1.Z = w1 - w0;
+        g1.A = (const char*)L + Ls[0] * w0 * es; g1.a_rs = Ls[1]; g1.a_ks = Ls[2]; g1.a_ps = 0; g1.a_zs = Ls[0]; g1.conjA = 0;
+        g1.B = d->theta; g1.b_rs = 1; g1.b_ks = N1; g1.b_ps = 0; g1.b_zs = 0; g1.conjB = 0;
+        g1.C = T1 + clo * N1 * w0 * es; g1.c_ms = N1; g1.c_ns = 1; g1.c_zs = clo * N1;
+        g1.force_path = 0;
+        if (d->n_chunks > 1) {       // fused all-gather -> GEMM: gate the k chunks on their arrival flags
+            if (!d->chunk_flags) return QSB_ERR_ARG;
+            g1.kepoch = d->chunk_epoch; g1.kflags = d->chunk_flags;
+            if (d->chunk_axis == 1) { g1.nsplit = d->n_chunks; }
+            else { g1.ksplit = d->n_chunks; g1.krot = d->chunk_rot; g1.klocal = d->chunk_local; }
+            g1.force_path = 1;
+        }
+        if ((rc = gemm_launch(g1, stream))) return rc;
+        w0 = w1;
     }
-    if ((rc = gemm_launch(g1, stream))) return rc;
     stage_mark(1, stream);
 
     // steps 2+3 (labels 2..5):  T3[a'][s1' s2'][w_r][b] = sum G[(w_r s1' s2'), (w s1 s2)] T1[w][a'][s1 s2][b]
+    // (rows of an identity channel of R are the finished contribution of that channel: they go straight to `out`)
     MixArgs ma{};
     ma.in = T1; ma.out = T3;
     ma.rowptr = pp.rowptr; ma.colofs = pp.colofs; ma.vals = pp.vals;
@@ -399,19 +432,97 @@ extern "C" int qsb_heff_apply(const qsb_heff_desc* d, void* stream_) {
     ma.o_s0 = cri; ma.o_s1 = (long long)d->W_r * cri;
     ma.i_us = N1; ma.o_us = dO * d->W_r * cri;
     ma.U = (int)clo; ma.X = (int)cri;
-    if ((rc = launch_mix(cplx, ma, stream))) return rc;
+    if (idR >= 0) { ma.id_ro = idR; ma.out2 = (char*)d->out; ma.o2_us = dO * cro; ma.o2_s1 = cro; }
+    if ((rc = launch_mix(cplx, ma, stream, (id_delta & 1) == 0))) return rc;
     stage_mark(2, stream);
 
     // step 4 (labels 6,7):  out[a' s1' s2'][b'] = sum_{w_r, b} T3[a' s1' s2'][w_r][b] R[w_r][b'][b]
-    GemmArgs g4{};
-    g4.cplx = cplx; g4.M = (int)(clo * dO); g4.N = (int)cro; g4.K = (int)cri; g4.P = d->W_r; g4.Z = 1;
-    g4.A = T3; g4.a_rs = (long long)d->W_r * cri; g4.a_ks = 1; g4.a_ps = cri; g4.a_zs = 0; g4.conjA = 0;
-    g4.B = R; g4.b_rs = Rs[1]; g4.b_ks = Rs[2]; g4.b_ps = Rs[0]; g4.b_zs = 0; g4.conjB = 0;
-    g4.C = d->out; g4.c_ms = cro; g4.c_ns = 1; g4.c_zs = 0;
-    g4.force_path = 0;
-    rc = gemm_launch(g4, stream);
+    // over the runs of non-identity panels, accumulating onto what the mix already put into `out`
+    bool have = idR >= 0;
+    for (int p0 = 0; p0 < d->W_r;) {
+        if (p0 == idR) { ++p0; continue; }
+        int p1 = p0;
+        while (p1 < d->W_r && p1 != idR) ++p1;
+        GemmArgs g4{};
+        g4.cplx = cplx; g4.M = (int)(clo * dO); g4.N = (int)cro; g4.K = (int)cri; g4.P = p1 - p0; g4.Z = 1;
+        g4.A = T3 + cri * p0 * es; g4.a_rs = (long long)d->W_r * cri; g4.a_ks = 1; g4.a_ps = cri; g4.a_zs = 0; g4.conjA = 0;
+        g4.B = (const char*)R + Rs[0] * p0 * es; g4.b_rs = Rs[1]; g4.b_ks = Rs[2]; g4.b_ps = Rs[0]; g4.b_zs = 0; g4.conjB = 0;
+        g4.C = d->out; g4.c_ms = cro; g4.c_ns = 1; g4.c_zs = 0;
+        g4.force_path = 0;
+        g4.accumulate = have ? 1 : 0;
+        if ((rc = gemm_launch(g4, stream))) return rc;
+        have = true;
+        p0 = p1;
+    }
     stage_mark(3, stream);
-    return rc;
+    return QSB_OK;
+}
+
+extern "C" double qsb_heff_flops_executed(const qsb_heff_desc* d) {
+    if (heff_check(d)) return 0.0;
+    const double c = d->dtype == QSB_C128 ? 8.0 : 2.0;
+    const double clo = d->chi_l_out, cli = d->chi_l_in, cro = d->chi_r_out, cri = d->chi_r_in;
+    const double dI = (double)d->d1_in * d->d2_in, dO = (double)d->d1_out * d->d2_out;
+    int idL = d->L_identity - 1, idR = d->R_identity - 1;
+    if (idL >= d->W_l || clo > cli) idL = -1;
+    if (idR >= d->W_r || cro != cri) idR = -1;
+    const double Wl = d->W_l - (idL >= 0 ? 1 : 0), Wr = d->W_r - (idR >= 0 ? 1 : 0);
+    const double dense = qsb_heff_flops(d);
+    const double g1_dense = c * d->W_l * clo * cli * dI * cri, g4_dense = c * cro * (d->W_r * cri) * (dO * clo);
+    return dense - g1_dense - g4_dense + c * Wl * clo * cli * dI * cri + c * cro * (Wr * cri) * (dO * clo);
+}
+
+// ---------------------------------------------------------------------------------------------
+// identity test of environment channels
+// ---------------------------------------------------------------------------------------------
+namespace qsb {
+template <bool CPLX>
+__global__ void __launch_bounds__(256) identity_dev_kernel(const char* env, long long s0, long long s1, long long s2,
+                                                           int rows, int cols, int row0, unsigned long long* maxdev) {
+    const int w = blockIdx.y;
+    const long long total = (long long)rows * cols;
+    double m = 0.0;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(e / cols), c = (int)(e - (long long)r * cols);
+        const long long o = w * s0 + r * s1 + c * s2;
+        const double want = (c == r + row0) ? 1.0 : 0.0;
+        double dv;
+        if constexpr (CPLX) {
+            const double2 v = reinterpret_cast<const double2*>(env)[o];
+            dv = fmax(fabs(v.x - want), fabs(v.y));
+        } else {
+            dv = fabs(reinterpret_cast<const double*>(env)[o] - want);
+        }
+        if (!(dv <= m)) m = dv;                          // NaN propagates as "not an identity"
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_xor_sync(0xffffffffu, m, o); if (!(t <= m)) m = t; }
+    if ((threadIdx.x & 31) == 0) {
+        if (m != m) m = 1e300;
+        atomicMax(maxdev + w, (unsigned long long)__double_as_longlong(m));    // non-negative doubles order as integers
+    }
+}
+}  // namespace qsb
+
+extern "C" int qsb_env_identity_deviation(int dtype, int W, int rows, int cols, const void* env, const int64_t stride[3],
+                                          int row0, double* maxdev, void* stream_) {
+    if (dtype != QSB_F64 && dtype != QSB_C128) return QSB_ERR_DTYPE;
+    if (!env || !stride || !maxdev) return QSB_ERR_ARG;
+    if (W < 1 || rows < 1 || cols < 1 || W > 65535) return QSB_ERR_SHAPE;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = check_cuda(cudaMemsetAsync(maxdev, 0, (size_t)W * sizeof(double), stream));
+    if (rc) return rc;
+    long long blocks = ((long long)rows * cols + 255) / 256;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    dim3 grid((unsigned)blocks, (unsigned)W);
+    if (dtype == QSB_C128)
+        identity_dev_kernel<true><<<grid, 256, 0, stream>>>((const char*)env, stride[0], stride[1], stride[2], rows, cols,
+                                                            row0, (unsigned long long*)maxdev);
+    else
+        identity_dev_kernel<false><<<grid, 256, 0, stream>>>((const char*)env, stride[0], stride[1], stride[2], rows, cols,
+                                                             row0, (unsigned long long*)maxdev);
+    ++g_count_other;
+    return check_launch();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -657,7 +768,28 @@ static int env_update(const qsb_env_desc* d, bool left, cudaStream_t stream) {
         g3.B = site; g3.b_rs = dd * ci; g3.b_ks = 1; g3.b_zs = 0;
         g3.C = d->out; g3.c_ms = co; g3.c_ns = 1; g3.c_zs = cb * co;
     }
-    if ((rc = gemm_launch(g1, stream))) return rc;
+    // identity-channel shortcut: T1[w] = conj(site) for the (verified) identity slice w of the old environment
+    int idE = d->env_identity - 1;
+    if (idE >= d->W_in || e.hasBra) idE = -1;
+    if (idE < 0) {
+        if ((rc = gemm_launch(g1, stream))) return rc;
+    } else {
+        const long long es = cplx ? 16 : 8;
+        const int64_t dims[3] = {left ? ci : co, dd, left ? co : ci};
+        const int64_t st[3] = {dims[1] * dims[2], dims[2], 1};
+        if ((rc = launch_copy3(cplx, dims, bra, st, T1 + slab * idE * es, 1, stream))) return rc;
+        for (int w0 = 0; w0 < d->W_in;) {
+            if (w0 == idE) { ++w0; continue; }
+            int w1 = w0;
+            while (w1 < d->W_in && w1 != idE) ++w1;
+            GemmArgs gr = g1;
+            gr.Z = w1 - w0;
+            if (left) gr.A = (const char*)g1.A + g1.a_zs * w0 * es; else gr.B = (const char*)g1.B + g1.b_zs * w0 * es;
+            gr.C = (char*)g1.C + g1.c_zs * w0 * es;
+            if ((rc = gemm_launch(gr, stream))) return rc;
+            w0 = w1;
+        }
+    }
     if ((rc = launch_mix(cplx, ma, stream))) return rc;
     return gemm_launch(g3, stream);
 }

@@ -59,6 +59,7 @@ struct KArgs {
     const char* B; long long b_rs, b_ks, b_ps, b_zs;
     char* C; long long c_ms, c_ns, c_zs;
     double sgnA, sgnB;              // -1 when the operand is conjugated (complex only)
+    int accum;                      // 1: C += A.B
 };
 
 // one operand tile: global -> shared with cp.async, zero fill outside [r_valid) x [k_valid)
@@ -244,6 +245,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_cpasync(const KArgs g) {
             if (n >= g.N) continue;
             char* dst = Cz + (g.c_ms * m + g.c_ns * n) * C::ES;
             if constexpr (!CPLX) {
+                if (g.accum) {
+                    acc[i][j][0] += *reinterpret_cast<const double*>(dst);
+                    if (n + 1 < g.N) acc[i][j][1] += *reinterpret_cast<const double*>(dst + g.c_ns * C::ES);
+                }
                 if (vec_ok && n + 1 < g.N) {
                     *reinterpret_cast<double2*>(dst) = make_double2(acc[i][j][0], acc[i][j][1]);
                 } else {
@@ -251,6 +256,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_cpasync(const KArgs g) {
                     if (n + 1 < g.N) *reinterpret_cast<double*>(dst + g.c_ns * C::ES) = acc[i][j][1];
                 }
             } else {
+                if (g.accum) {
+                    const double2 o0 = *reinterpret_cast<const double2*>(dst);
+                    acc[i][j][0] += o0.x; acc[i][j][2] += o0.y;
+                    if (n + 1 < g.N) {
+                        const double2 o1 = *reinterpret_cast<const double2*>(dst + g.c_ns * C::ES);
+                        acc[i][j][1] += o1.x; acc[i][j][3] += o1.y;
+                    }
+                }
                 *reinterpret_cast<double2*>(dst) = make_double2(acc[i][j][0], acc[i][j][2]);
                 if (n + 1 < g.N)
                     *reinterpret_cast<double2*>(dst + g.c_ns * C::ES) = make_double2(acc[i][j][1], acc[i][j][3]);
@@ -305,6 +318,7 @@ int gemm_launch(const GemmArgs& g, cudaStream_t stream) {
     k.B = (const char*)g.B; k.b_rs = g.b_rs; k.b_ks = g.b_ks; k.b_ps = g.b_ps; k.b_zs = g.b_zs;
     k.C = (char*)g.C; k.c_ms = g.c_ms; k.c_ns = g.c_ns; k.c_zs = g.c_zs;
     k.sgnA = g.conjA ? -1.0 : 1.0; k.sgnB = g.conjB ? -1.0 : 1.0;
+    k.accum = g.accumulate;
     // extent-1 dimensions carry arbitrary strides in torch: normalise them
     if (g.K == 1) { k.a_ks = 1; k.b_ks = 1; }
     if (g.M == 1 && k.a_ks != 1) k.a_rs = 1;
@@ -374,6 +388,7 @@ extern "C" int qsb_gemm(const qsb_gemm_desc* d, void* stream) {
     g.B = d->B; g.b_rs = d->b_ns; g.b_ks = d->b_ks; g.b_ps = d->b_ps; g.b_zs = d->b_zs; g.conjB = d->conjB;
     g.C = d->C; g.c_ms = d->c_ms; g.c_ns = d->c_ns; g.c_zs = d->c_zs;
     g.force_path = d->force_path;
+    g.accumulate = d->accumulate;
     if (g.P < 1) g.P = 1;
     return gemm_launch(g, (cudaStream_t)stream);
 }

@@ -200,11 +200,14 @@ constexpr int kAccPerThread = 64;
 
 // GATED instantiations carry the arrival-gating code (fused multi-GPU exchange, host upload); the plain ones do
 // not: the kernel sits at the register limit and any extra live value perturbs the main loop (measured: 3 %).
-template <bool CPLX, bool A_KC, bool B_KC, bool GATED>
+// ACCUM instantiations add the tile to what C already holds (C += A.B): the identity-channel shortcut of the H_eff
+// matvec pre-loads C with the panel whose environment slice is the identity and the GEMM runs over the other panels.
+template <bool CPLX, bool A_KC, bool B_KC, int VARIANT>
 __global__ void __launch_bounds__(kTmaThreads, 1)
 gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TArgs g,
                 const SkArgs sk) {
     using C = TCfg<CPLX>;
+    constexpr bool GATED = VARIANT == 1, ACCUM = VARIANT == 2;
     constexpr int A_BYTES = C::BM * C::BK * C::ES;
     constexpr int B_BYTES = C::BN * C::BK * C::ES;
     constexpr int STAGE = A_BYTES + B_BYTES;
@@ -436,14 +439,33 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 char* row = Cz + g.c_ms * m * C::ES;
                 if constexpr (!CPLX) {
                     if (vec_ok && c1 < g.N) {        // c1 == c0 + 1 for the RC permutation
-                        *reinterpret_cast<double2*>(row + (long long)c0 * C::ES) = make_double2(acc[i][j][0], acc[i][j][1]);
+                        double2* dst = reinterpret_cast<double2*>(row + (long long)c0 * C::ES);
+                        double2 v = make_double2(acc[i][j][0], acc[i][j][1]);
+                        if constexpr (ACCUM) { const double2 o = *dst; v.x += o.x; v.y += o.y; }
+                        *dst = v;
                     } else {
-                        if (c0 < g.N) *reinterpret_cast<double*>(row + g.c_ns * c0 * C::ES) = acc[i][j][0];
-                        if (c1 < g.N) *reinterpret_cast<double*>(row + g.c_ns * c1 * C::ES) = acc[i][j][1];
+                        if (c0 < g.N) {
+                            double* dst = reinterpret_cast<double*>(row + g.c_ns * c0 * C::ES);
+                            *dst = ACCUM ? acc[i][j][0] + *dst : acc[i][j][0];
+                        }
+                        if (c1 < g.N) {
+                            double* dst = reinterpret_cast<double*>(row + g.c_ns * c1 * C::ES);
+                            *dst = ACCUM ? acc[i][j][1] + *dst : acc[i][j][1];
+                        }
                     }
                 } else {
-                    if (c0 < g.N) *reinterpret_cast<double2*>(row + g.c_ns * c0 * C::ES) = make_double2(acc[i][j][0], acc[i][j][2]);
-                    if (c1 < g.N) *reinterpret_cast<double2*>(row + g.c_ns * c1 * C::ES) = make_double2(acc[i][j][1], acc[i][j][3]);
+                    if (c0 < g.N) {
+                        double2* dst = reinterpret_cast<double2*>(row + g.c_ns * c0 * C::ES);
+                        double2 v = make_double2(acc[i][j][0], acc[i][j][2]);
+                        if constexpr (ACCUM) { const double2 o = *dst; v.x += o.x; v.y += o.y; }
+                        *dst = v;
+                    }
+                    if (c1 < g.N) {
+                        double2* dst = reinterpret_cast<double2*>(row + g.c_ns * c1 * C::ES);
+                        double2 v = make_double2(acc[i][j][1], acc[i][j][3]);
+                        if constexpr (ACCUM) { const double2 o = *dst; v.x += o.x; v.y += o.y; }
+                        *dst = v;
+                    }
                 }
             }
         }
@@ -547,10 +569,10 @@ static int sk_scratch(SkScratch** out) {
     return QSB_OK;
 }
 
-template <bool CPLX, bool A_KC, bool B_KC, bool GATED>
+template <bool CPLX, bool A_KC, bool B_KC, int VARIANT>
 static int launch_tma_g(const CUtensorMap& ma, const CUtensorMap& mb, const TArgs& t, int Z, cudaStream_t stream) {
     using C = TCfg<CPLX>;
-    auto kern = gemm_tma_kernel<CPLX, A_KC, B_KC, GATED>;
+    auto kern = gemm_tma_kernel<CPLX, A_KC, B_KC, VARIANT>;
     constexpr int SMEM = C::STAGES * (C::BM + C::BN) * C::BK * C::ES + 2 * C::STAGES * 8 + 1024;
     static bool configured[64] = {};         // per instantiation and device (the attribute is per device)
     int dev = 0;
@@ -589,9 +611,14 @@ static int launch_tma_g(const CUtensorMap& ma, const CUtensorMap& mb, const TArg
 }
 
 template <bool CPLX, bool A_KC, bool B_KC>
-static int launch_tma(const CUtensorMap& ma, const CUtensorMap& mb, const TArgs& t, int Z, cudaStream_t stream) {
-    if (t.ksplit > 1 || t.nsplit > 1) return launch_tma_g<CPLX, A_KC, B_KC, true>(ma, mb, t, Z, stream);
-    return launch_tma_g<CPLX, A_KC, B_KC, false>(ma, mb, t, Z, stream);
+static int launch_tma(const CUtensorMap& ma, const CUtensorMap& mb, const TArgs& t, int Z, cudaStream_t stream,
+                      bool accumulate) {
+    if (t.ksplit > 1 || t.nsplit > 1) {
+        if (accumulate) return QSB_ERR_ARG;          // no caller needs a gated accumulating GEMM
+        return launch_tma_g<CPLX, A_KC, B_KC, 1>(ma, mb, t, Z, stream);
+    }
+    if (accumulate) return launch_tma_g<CPLX, A_KC, B_KC, 2>(ma, mb, t, Z, stream);
+    return launch_tma_g<CPLX, A_KC, B_KC, 0>(ma, mb, t, Z, stream);
 }
 
 int gemm_tma_try(const GemmArgs& g, cudaStream_t stream, bool* used) {
@@ -637,12 +664,13 @@ int gemm_tma_try(const GemmArgs& g, cudaStream_t stream, bool* used) {
         t.nsplit = g.nsplit; t.kepoch = g.kepoch; t.kflags = g.kflags;
     }
     int rc;
+    const bool acc = g.accumulate != 0;
     if (cplx) {
-        if (a_kc) rc = b_kc ? launch_tma<true, true, true>(ma, mb, t, g.Z, stream) : launch_tma<true, true, false>(ma, mb, t, g.Z, stream);
-        else rc = b_kc ? launch_tma<true, false, true>(ma, mb, t, g.Z, stream) : launch_tma<true, false, false>(ma, mb, t, g.Z, stream);
+        if (a_kc) rc = b_kc ? launch_tma<true, true, true>(ma, mb, t, g.Z, stream, acc) : launch_tma<true, true, false>(ma, mb, t, g.Z, stream, acc);
+        else rc = b_kc ? launch_tma<true, false, true>(ma, mb, t, g.Z, stream, acc) : launch_tma<true, false, false>(ma, mb, t, g.Z, stream, acc);
     } else {
-        if (a_kc) rc = b_kc ? launch_tma<false, true, true>(ma, mb, t, g.Z, stream) : launch_tma<false, true, false>(ma, mb, t, g.Z, stream);
-        else rc = b_kc ? launch_tma<false, false, true>(ma, mb, t, g.Z, stream) : launch_tma<false, false, false>(ma, mb, t, g.Z, stream);
+        if (a_kc) rc = b_kc ? launch_tma<false, true, true>(ma, mb, t, g.Z, stream, acc) : launch_tma<false, true, false>(ma, mb, t, g.Z, stream, acc);
+        else rc = b_kc ? launch_tma<false, false, true>(ma, mb, t, g.Z, stream, acc) : launch_tma<false, false, false>(ma, mb, t, g.Z, stream, acc);
     }
     if (rc) return rc;
     *used = true;

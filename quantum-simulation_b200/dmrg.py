@@ -143,7 +143,11 @@ class ApplyMPO(_BaseContractModule):
             res = out.view(-1)
         else:
             res = torch.empty(n_out, device=psi.device, dtype=psi.dtype)
-        _lib.ops.heff_apply(psi.view(-1), L, M1, M2, R, res)
+        (li, lrow0), (ri, _r0) = _lib.identity_of(L), _lib.identity_of(R)
+        if li >= 0 or ri >= 0:         # verified identity channels: their chi^3 GEMM slices are skipped
+            _lib.ops.heff_apply_ident(psi.view(-1), L, M1, M2, R, res, li, ri, lrow0)
+        else:
+            _lib.ops.heff_apply(psi.view(-1), L, M1, M2, R, res)
         return res
 
 
@@ -160,6 +164,7 @@ class ApplyMPO(_BaseContractModule):
         blocks of the left bond and each finished block is downloaded on a second copy stream while the next one
         computes.  Compute stays on the GPU -- this is
         not a CPU fallback; unpinned host tensors are rejected."""
+        (li, lrow0), (ri, _r0) = _lib.identity_of(L), _lib.identity_of(R)
         L, M1, M2, R = (_dev_tensor(t) for t in (L, M1, M2, R))
         M1, M2 = M1.contiguous(), M2.contiguous()
         dev = L.device
@@ -228,18 +233,27 @@ class ApplyMPO(_BaseContractModule):
             for b in range(n_blocks):
                 Lb = L[:, b * rows:(b + 1) * rows, :]
                 ob = out_dev[b * rows * per_out:(b + 1) * rows * per_out]
-                if mode != "plain":
+                row0 = lrow0 + b * rows                    # an identity channel of L, seen from this row block
+                if mode == "col":
                     try:
-                        if mode == "col":
-                            _lib.ops.heff_apply_colgated(theta_dev, Lb, M1, M2, R, ob, pipe["flags"], col_chunks, epoch)
-                        else:
-                            _lib.ops.heff_apply_gated(theta_dev, Lb, M1, M2, R, ob, pipe["flags"], row_chunks, 0, epoch, 0)
+                        # (the identity shortcut stays valid under gating: the step-1 GEMM of the other channels reads
+                        # every block of theta, so all of it has landed before the mix reads theta in place)
+                        _lib.ops.heff_apply_colgated(theta_dev, Lb, M1, M2, R, ob, pipe["flags"], col_chunks, epoch,
+                                                     li, ri, row0)
                     except ValueError:                     # operands the TMA-staged (gated) GEMM cannot describe
                         main.wait_stream(pipe["h2d"])
                         mode = "plain"
-                        _lib.ops.heff_apply(theta_dev, Lb, M1, M2, R, ob)
+                        _lib.ops.heff_apply_ident(theta_dev, Lb, M1, M2, R, ob, li, ri, row0)
+                elif mode == "row":
+                    try:
+                        _lib.ops.heff_apply_gated(theta_dev, Lb, M1, M2, R, ob, pipe["flags"], row_chunks, 0, epoch, 0,
+                                                  li, ri, row0)
+                    except ValueError:
+                        main.wait_stream(pipe["h2d"])
+                        mode = "plain"
+                        _lib.ops.heff_apply_ident(theta_dev, Lb, M1, M2, R, ob, li, ri, row0)
                 else:
-                    _lib.ops.heff_apply(theta_dev, Lb, M1, M2, R, ob)
+                    _lib.ops.heff_apply_ident(theta_dev, Lb, M1, M2, R, ob, li, ri, row0)
                 done = torch.cuda.Event()
                 done.record(main)
                 pipe["d2h"].wait_event(done)
@@ -259,9 +273,10 @@ class LeftEnvUpdate(_BaseContractModule):
         Lp, M, Ap = (_dev_tensor(t) for t in (Lp, M, Ap))
         if not M.is_contiguous():
             M = M.contiguous()
+        ident = _lib.identity_of(Lp)[0]
         out = torch.empty(M.shape[1], Ap.shape[2], Ap.shape[2], device=Lp.device, dtype=Lp.dtype)
-        _lib.ops.env_left(Lp, M, Ap, out)
-        return out
+        _lib.ops.env_left(Lp, M, Ap, out, ident)
+        return _lib.tag_identity(out)
 
 
 class RightEnvUpdate(_BaseContractModule):
@@ -272,9 +287,10 @@ class RightEnvUpdate(_BaseContractModule):
         M, Rnext, Bp1 = (_dev_tensor(t) for t in (M, Rnext, Bp1))
         if not M.is_contiguous():
             M = M.contiguous()
+        ident = _lib.identity_of(Rnext)[0]
         out = torch.empty(M.shape[0], Bp1.shape[0], Bp1.shape[0], device=Rnext.device, dtype=Rnext.dtype)
-        _lib.ops.env_right(Rnext, M, Bp1, out)
-        return out
+        _lib.ops.env_right(Rnext, M, Bp1, out, ident)
+        return _lib.tag_identity(out)
 
 
 class EnvironmentManager:

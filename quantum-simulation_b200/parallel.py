@@ -18,7 +18,7 @@ import torch
 
 from .eigensolver import _lanczos_impl, _CUDA_OPS
 
-__all__ = ["row_partition", "ShardedApplyMPO", "lanczos_ground_state_sharded", "shard_rows", "gather_rows",
+__all__ = ["row_partition", "fused_eligible", "ShardedApplyMPO", "lanczos_ground_state_sharded", "shard_rows", "gather_rows",
            "ShardedDMRG", "CudaEngine", "FusedShardedApplyMPO", "SymmetricArena"]
 
 
@@ -136,6 +136,17 @@ class SymmetricArena:
         dist.barrier(group=self.group)
 
 
+def fused_eligible(chi_l: int, per_row: int, dtype: torch.dtype, world: int) -> bool:
+    """Can the arrival-gated (TMA-staged) step-1 GEMM describe this bond?  The k range (chi_l) must split into
+    ``world`` chunks of whole BK-deep k-tiles, and theta viewed as (chi_l, per_row) -- the operand whose ROW index is
+    contiguous -- needs per_row to be a multiple of one 128-byte line (16 float64 / 8 complex128), see
+    csrc/gemm_tma.cu ``tma_eligible``.  A cutoff-truncated or spin-1 right bond (e.g. chi_r = 50 or 27) fails the
+    second condition; such bonds take the all-gather + plain matvec path (``ShardedApplyMPO``)."""
+    bk = 8 if dtype.is_complex else 16
+    line = 8 if dtype.is_complex else 16
+    return world >= 1 and chi_l % (bk * world) == 0 and per_row % line == 0
+
+
 class FusedShardedApplyMPO:
     """Sharded H_eff . theta with the all-gather FUSED into the matvec (no NCCL call on the data path).
 
@@ -161,9 +172,10 @@ class FusedShardedApplyMPO:
         world = dist.get_world_size(grp)
         es = torch.empty(0, dtype=dtype).element_size()
         bk = 8 if dtype.is_complex else 16
-        if chi_l % world != 0 or (chi_l // bk) % world != 0 or chi_l % bk != 0:
-            raise ValueError(f"fused sharded matvec needs chi_l divisible by {bk} * world_size (got chi_l={chi_l}, "
-                             f"world={world}); use ShardedApplyMPO")
+        if not fused_eligible(chi_l, per_row, dtype, world):
+            raise ValueError(f"fused sharded matvec needs chi_l divisible by {bk} * world_size and d1*d2*chi_r "
+                             f"divisible by {bk} (got chi_l={chi_l}, per_row={per_row}, world={world}); "
+                             "use ShardedApplyMPO")
         n = chi_l * per_row
         if arena is None:
             arena = SymmetricArena(n * es, device, grp)
@@ -198,10 +210,11 @@ class FusedShardedApplyMPO:
             v = v.contiguous()
         if out is None:
             out = torch.empty(L_rows.shape[1] * M1.shape[2] * M2.shape[2] * R.shape[1], dtype=v.dtype, device=v.device)
+        (li, lrow0), (ri, _r0) = self._lib.identity_of(L_rows), self._lib.identity_of(R)   # verified identity channels
         if self.push == "sm":
             self._ops.push_shard(v, self.dst_ptrs[b], self.flag_ptrs, self.epoch, self.ticket)
             self._ops.heff_apply_gated(self.bufs[b], L_rows, M1, M2, R, out, self.flags, self.world, self.rank,
-                                       self.epoch, 0)
+                                       self.epoch, 0, li, ri, lrow0)
             return out
         # copy engines on a side stream: the pushes run WHILE the gated GEMM already works on the local block
         main = torch.cuda.current_stream(v.device)
@@ -224,7 +237,8 @@ class FusedShardedApplyMPO:
                 done = torch.cuda.Event()
                 done.record(side)
                 dones.append(done)
-        self._ops.heff_apply_gated(self.bufs[b], L_rows, M1, M2, R, out, self.flags, self.world, self.rank, self.epoch, 1)
+        self._ops.heff_apply_gated(self.bufs[b], L_rows, M1, M2, R, out, self.flags, self.world, self.rank, self.epoch, 1,
+                                   li, ri, lrow0)
         for done in dones:
             main.wait_event(done)        # v_shard may be reused once our outgoing copies have left
         return out
@@ -288,6 +302,13 @@ class CudaEngine:
     def split(self, theta2d, maxdim, cutoff):
         from .svd import two_site_split
         return two_site_split(theta2d, maxdim, cutoff)
+
+    def tag(self, env, row0=0):
+        """Test an environment (or this rank's row block of one, first row ``row0``) for an identity channel and
+        record the answer on the tensor: the matvec kernels skip the chi^3 GEMM slice of such a channel."""
+        if self._lib.identity_of(env)[0] < 0:
+            self._lib.tag_identity(env, row0)
+        return env
 
     def lanczos(self, v, op, args, **kw):
         from .eigensolver import lanczos_ground_state
@@ -378,12 +399,16 @@ class ShardedDMRG:
         lo, hi = self._block(e.chi)
         return e.t[:, lo:hi, :]
 
+    def _tag(self, t: torch.Tensor, row0: int = 0) -> torch.Tensor:
+        tag = getattr(self.engine, "tag", None)           # the CPU engines of the gloo tests have no such shortcut
+        return tag(t, row0) if tag is not None else t
+
     def _store(self, full: torch.Tensor) -> _Env:
         chi = full.shape[1]
         if self._shardable(chi):
             lo, hi = self._block(chi)
-            return _Env(full[:, lo:hi, :].contiguous(), True, chi)
-        return _Env(full, False, chi)
+            return _Env(self._tag(full[:, lo:hi, :].contiguous(), lo), True, chi)
+        return _Env(self._tag(full), False, chi)
 
     # ---- environment updates ---------------------------------------------------------------------------
     def _update_L(self, Lp: _Env, M: torch.Tensor, A: torch.Tensor) -> _Env:
@@ -405,10 +430,11 @@ class ShardedDMRG:
             else:                                         # NCCL reduces real dtypes only: (re, im) pairs
                 dist.reduce_scatter_tensor(_real_view(recv), _real_view(send.view(-1)), group=self.group)
             self.comm["reduce_scatter_env"] += 1
-            return _Env(recv.view(rows, Wn, chi_new).permute(1, 0, 2), True, chi_new)   # strided view, last dim contiguous
+            new = recv.view(rows, Wn, chi_new).permute(1, 0, 2)                 # strided view, last dim contiguous
+            return _Env(self._tag(new, self._block(chi_new)[0]), True, chi_new)
         dist.all_reduce(_real_view(partial), group=self.group)
         self.comm["all_reduce_env"] += 1
-        return _Env(partial, False, chi_new)
+        return _Env(self._tag(partial), False, chi_new)
 
     def _update_R(self, M: torch.Tensor, Rn_full: torch.Tensor, B: torch.Tensor) -> _Env:
         chi_new = B.shape[0]
@@ -440,8 +466,8 @@ class ShardedDMRG:
         key = (chi_l, per_row, dtype)
         op = self._ops_cache.get(key)
         if op is None:
-            bk = 8 if dtype.is_complex else 16
-            if self.use_fused and isinstance(self.engine, CudaEngine) and chi_l % (bk * self.world) == 0:
+            if self.use_fused and isinstance(self.engine, CudaEngine) \
+                    and fused_eligible(chi_l, per_row, dtype, self.world):
                 es = torch.empty(0, dtype=dtype).element_size()
                 if self._arena is None or self._arena.stride < chi_l * per_row * es:
                     # one symmetric allocation for the largest vector this run can see (maxdim^2 d^2)
@@ -506,7 +532,7 @@ class ShardedDMRG:
                 psi = self.engine.matmul(lt.reshape(l * s, m), torch.mul(rt, sw.to(rt.dtype).view(1, 1, -1)).reshape(m, t * r))
             chil, chir = l, r
             self._tick("theta")
-            R_full = self._full(R[p + 2])
+            R_full = self._tag(self._full(R[p + 2]))
             self._tick("gather_R")
             theta, E = self._ground_state(psi, L[p], self.Ms[p], self.Ms[p + 1], R_full, chil, kw)
             self._tick("lanczos")

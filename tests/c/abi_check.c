@@ -8,7 +8,11 @@
 #define CHECK(cond) do { if (!(cond)) { fprintf(stderr, "abi_check failed: %s (line %d)\n", #cond, __LINE__); return 1; } } while (0)
 
 int main(void) {
-    CHECK(qsb_version() >= 100);
+    CHECK(qsb_version() >= 200);
+    /* the structs this translation unit sees are the structs the library was built with */
+    CHECK(qsb_sizeof_heff_desc() == sizeof(qsb_heff_desc));
+    CHECK(qsb_sizeof_env_desc() == sizeof(qsb_env_desc));
+    CHECK(qsb_sizeof_gemm_desc() == sizeof(qsb_gemm_desc));
     CHECK(strcmp(qsb_status_string(QSB_OK), "ok") == 0);
     CHECK(strlen(qsb_status_string(QSB_ERR_WORKSPACE)) > 0);
 
@@ -27,7 +31,13 @@ int main(void) {
     CHECK(bytes >= 2ull * 5 * 4 * 2048 * 2048 * 8);                     /* T1 + T3 at BASELINE config 3 */
     double flops = qsb_heff_flops(&d);
     CHECK(flops > 6.90e11 && flops < 6.92e11);                          /* 6.906e11 */
+    CHECK(qsb_heff_flops_executed(&d) == flops);                        /* no identity channel declared */
+    d.L_identity = 5; d.R_identity = 1;                                 /* 1 + channel: L[4], R[0] (FSM layout) */
+    double ex = qsb_heff_flops_executed(&d);
+    CHECK(flops - ex == 2.0 * 2.0 * 4.0 * 2048.0 * 2048.0 * 2048.0);    /* one chi^3 d^2 GEMM slice per side */
+    d.L_identity = d.R_identity = 0;
     CHECK(qsb_heff_apply(&d, NULL) == QSB_ERR_ARG);                     /* null data pointers, no launch */
+    CHECK(qsb_env_identity_deviation(QSB_F64, 5, 8, 8, NULL, NULL, 0, NULL, NULL) == QSB_ERR_ARG);
     d.dtype = QSB_F32;
     CHECK(qsb_heff_apply(&d, NULL) == QSB_ERR_DTYPE);
 

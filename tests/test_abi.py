@@ -19,7 +19,11 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in qsb200.h but not exported"
     assert sorted(_lib.EXPORTS) == declared
-    assert lib.qsb_version() >= 100
+    assert lib.qsb_version() >= 200
+    import ctypes as C
+    for fn, st in ((lib.qsb_sizeof_heff_desc, _lib.HeffDesc), (lib.qsb_sizeof_env_desc, _lib.EnvDesc),
+                   (lib.qsb_sizeof_gemm_desc, _lib.GemmDesc)):
+        assert fn() == C.sizeof(st)          # the ctypes mirrors are byte-identical to include/qsb200.h
     assert _lib.status_string(0) == "ok" and "workspace" in _lib.status_string(5)
     c = qsb.launch_counters(reset=True)
     assert c["total"] == 0

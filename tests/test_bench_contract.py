@@ -42,6 +42,9 @@ def test_our_arm_contract_gpu():
     assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and 0 < r["frac"] < 1.2 and r["peak"] > 10
     assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
     assert d["gpu_launches"] == 3 * 4                 # prepare + GEMM + mix + GEMM per step
+    assert d["executed"]["identity_channels"] == {"L": 4, "R": 0}          # canonical-gauge environments (FSM layout)
+    assert d["executed"]["tflops"] < d["tflops"] and r["channels_executed"]["step1"] == 4
+    assert "exchange" not in d["config"]              # both arms print the same config
     assert d["e2e"]["h2d_bytes_per_step"] == 256 * 4 * 256 * 8 and d["e2e"]["value"] < d["value"] * 1.05
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
     assert d["n_gpus"] == 1 and d["dtype"] == "f64" and d["vs_baseline"] is None

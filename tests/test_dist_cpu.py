@@ -186,3 +186,17 @@ def test_row_partition():
     assert row_partition(2048, 8)[7] == (1792, 2048)
     with pytest.raises(ValueError):
         row_partition(4, 0)
+
+
+def test_fused_exchange_eligibility():
+    """ADVICE r01 (medium): the fused (arrival-gated, TMA-staged) matvec is only chosen for bonds the TMA can describe;
+    truncated / spin-1 right bonds fall back to all-gather + plain matvec instead of aborting the sweep."""
+    import torch
+    from quantum_simulation_b200.parallel import fused_eligible
+    f64, c128 = torch.float64, torch.complex128
+    assert fused_eligible(2048, 4 * 2048, f64, 8) and fused_eligible(512, 16 * 512, c128, 8)
+    assert not fused_eligible(64, 4 * 50, f64, 2)          # chi_r = 50: 200 is not a multiple of 16
+    assert not fused_eligible(64, 9 * 27, f64, 2)          # spin-1, chi_r = 27
+    assert fused_eligible(64, 4 * 50, c128, 2)             # 200 % 8 == 0 for complex128
+    assert not fused_eligible(72, 4 * 64, f64, 8)          # k range does not split into whole k-tiles per rank
+    assert not fused_eligible(64, 4 * 64, c128, 16) and fused_eligible(128, 4 * 64, c128, 16)

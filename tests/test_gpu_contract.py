@@ -334,3 +334,185 @@ def test_environment_manager_chain_matches_oracle():
 def test_native_library_was_used():
     c = qsb.launch_counters()
     assert c["total"] > 0 and (c["cpasync_gemm"] + c["tma_gemm"]) > 0
+
+
+# ----------------------------------------------------------------------------- identity-channel shortcut
+def _with_identity(env, w, row0=0):
+    """Replace channel w of an environment (W, rows, cols) by the (row-shifted) identity, plus rounding-level noise
+    of the size a real A^H A carries."""
+    env = env.clone()
+    rows, cols = env.shape[1:]
+    eye = torch.zeros(rows, cols, dtype=env.dtype)
+    eye[torch.arange(rows), torch.arange(rows) + row0] = 1.0
+    env[w] = eye + 1e-16 * randn((rows, cols), env.dtype, 77)
+    return env
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.complex128])
+@pytest.mark.parametrize("chi_l,chi_r,wl_id,wr_id,layout", [
+    (64, 64, 0, 4, "contig"),       # the FSM pattern: first channel of L, last channel of R
+    (128, 96, 0, 4, "ncon"),        # TMA-eligible, reference's strided environments
+    (130, 70, 0, 4, "contig"),      # ragged -> cp.async GEMM + accumulate
+    (48, 40, 2, 1, "contig"),       # identity channels in the middle: two runs of panels each side
+    (32, 32, 0, None, "contig"),    # only L
+    (32, 32, None, 4, "ncon"),      # only R
+    (17, 5, 4, 0, "contig"),
+])
+def test_matvec_identity_channels(dtype, chi_l, chi_r, wl_id, wr_id, layout):
+    """MPO-sparsity-aware block skipping in the chi^3 GEMMs: with verified identity slices in L and/or R the
+    result equals the dense computation of the oracle (the reference has no such shortcut)."""
+    key = "heis_c128_L20" if dtype.is_complex else "heis_f64_L20"
+    Ms = golden_mpo(key, dtype)
+    M1, M2 = Ms[9], Ms[10]
+    L = randn((5, chi_l, chi_l), dtype, 11)
+    R = randn((5, chi_r, chi_r), dtype, 12)
+    if wl_id is not None:
+        L = _with_identity(L, wl_id)
+    if wr_id is not None:
+        R = _with_identity(R, wr_id)
+    psi = randn((chi_l * 4 * chi_r,), dtype, 13)
+    ref = orc.apply_mpo(psi, L, M1, M2, R)
+    Ld, Rd = L.to(DEV), R.to(DEV)
+    if layout == "ncon":
+        Ld, Rd = ncon_layout(Ld), ncon_layout(Rd)
+    _lib.tag_identity(Ld)
+    _lib.tag_identity(Rd)
+    assert _lib.identity_of(Ld)[0] == (-1 if wl_id is None else wl_id)
+    assert _lib.identity_of(Rd)[0] == (-1 if wr_id is None else wr_id)
+    op = qsb.ApplyMPO()
+    before = qsb.launch_counters()
+    out = op(psi.to(DEV), Ld, M1.to(DEV), M2.to(DEV), Rd)
+    after = qsb.launch_counters()
+    assert rel_err(out, ref) <= TOL
+    # flop accounting: executed < dense exactly by the skipped slices
+    ident = (-1 if wl_id is None else wl_id, -1 if wr_id is None else wr_id, 0)
+    dense = _lib.heff_flops(psi.to(DEV), Ld, M1.to(DEV), M2.to(DEV), Rd)
+    execd = _lib.heff_flops_executed(psi.to(DEV), Ld, M1.to(DEV), M2.to(DEV), Rd, ident)
+    c = 8.0 if dtype.is_complex else 2.0
+    skipped = c * 4 * (chi_l ** 2 * chi_r * (wl_id is not None) + chi_r ** 2 * chi_l * (wr_id is not None))
+    assert abs((dense - execd) - skipped) <= 1e-9 * dense
+    # GEMM launches: one per run of dense channels on each side
+    runs = lambda W, i: 1 if i is None or i in (0, W - 1) else 2
+    gemms = (after["tma_gemm"] + after["cpasync_gemm"]) - (before["tma_gemm"] + before["cpasync_gemm"])
+    assert gemms == runs(5, wl_id) + runs(5, wr_id)
+    # an in-place write invalidates the tag (the shortcut must never act on stale knowledge)
+    if wl_id is not None:
+        Ld.mul_(2.0)
+        assert _lib.identity_of(Ld)[0] == -1
+        out2 = op(psi.to(DEV), Ld, M1.to(DEV), M2.to(DEV), Rd)
+        L2 = L.clone() * 2.0
+        assert rel_err(out2, orc.apply_mpo(psi, L2, M1, M2, R)) <= TOL
+
+
+def test_matvec_identity_single_channel_boundaries():
+    """W = 1 on a side whose only slice is the identity: no GEMM is launched on that side at all (chain ends,
+    where the reference's boundary environments are ones(W, 1, 1), dmrg.py:349-351)."""
+    dt = torch.float64
+    Ms = golden_mpo("heis_f64_L20", dt)
+    M1, M2 = Ms[0], Ms[1]                     # (1, 5, 2, 2), (5, 5, 2, 2)
+    L = torch.ones(1, 1, 1, dtype=dt)
+    R = _with_identity(randn((5, 24, 24), dt, 3), 4)
+    psi = randn((1 * 4 * 24,), dt, 4)
+    ref = orc.apply_mpo(psi, L, M1, M2, R)
+    Ld, Rd = _lib.tag_identity(L.to(DEV)), _lib.tag_identity(R.to(DEV))
+    assert _lib.identity_of(Ld)[0] == 0 and _lib.identity_of(Rd)[0] == 4
+    out = qsb.ApplyMPO()(psi.to(DEV), Ld, M1.to(DEV), M2.to(DEV), Rd)
+    assert rel_err(out, ref) <= TOL
+    # mirror image: last bond
+    M1, M2 = Ms[18], Ms[19]
+    L = _with_identity(randn((5, 24, 24), dt, 5), 0)
+    R = torch.ones(1, 1, 1, dtype=dt)
+    psi = randn((24 * 4,), dt, 6)
+    ref = orc.apply_mpo(psi, L, M1, M2, R)
+    out = qsb.ApplyMPO()(psi.to(DEV), _lib.tag_identity(L.to(DEV)), M1.to(DEV), M2.to(DEV), _lib.tag_identity(R.to(DEV)))
+    assert rel_err(out, ref) <= TOL
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.complex128])
+def test_identity_deviation_kernel(dtype):
+    W, rows, cols, row0 = 4, 48, 80, 16
+    env = randn((W, rows, cols), dtype, 21)
+    env = _with_identity(env, 2, row0)
+    dev_env = ncon_layout(env.to(DEV)) if dtype.is_complex else env.to(DEV)
+    assert _lib.identity_channel(dev_env, row0) == 2
+    assert _lib.identity_channel(dev_env, 0) == -1                 # wrong shift -> not an identity
+    assert _lib.identity_channel(dev_env, row0, tol=0.0) == -1     # disabled
+    bad = env.clone()
+    bad[2, 5, 7] += 1e-9
+    assert _lib.identity_channel(bad.to(DEV), row0) == -1
+    nan = env.clone()
+    nan[2, 1, 1] = float("nan")
+    assert _lib.identity_channel(nan.to(DEV), row0) == -1
+    if dtype.is_complex:
+        im = env.clone()
+        im[2, 3, 3 + row0] += 1e-6j
+        assert _lib.identity_channel(im.to(DEV), row0) == -1
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.complex128])
+@pytest.mark.parametrize("w_id", [0, 2, 4])
+def test_env_update_identity_input(dtype, w_id):
+    """Environment updates with a verified identity slice in the old environment (its GEMM becomes a copy) against
+    the oracle; the output of an isometric site tensor is tagged as carrying an identity channel in turn."""
+    key = "heis_c128_L20" if dtype.is_complex else "heis_f64_L20"
+    M = golden_mpo(key, dtype)[9]
+    chi, chip = 40, 24
+    A = randn((chi, 2, chip), dtype, 31)
+    B = randn((chip, 2, chi), dtype, 32)
+    Lp = _with_identity(randn((5, chi, chi), dtype, 33), w_id)
+    Rn = _with_identity(randn((5, chi, chi), dtype, 34), w_id)
+    refL = orc.left_env_update(Lp, M, A)
+    refR = orc.right_env_update(M, Rn, B)
+    Lpd, Rnd = _lib.tag_identity(Lp.to(DEV)), _lib.tag_identity(Rn.to(DEV))
+    assert _lib.identity_of(Lpd)[0] == w_id
+    outL = qsb.LeftEnvUpdate()(Lpd, M.to(DEV), A.to(DEV))
+    outR = qsb.RightEnvUpdate()(M.to(DEV), Rnd, B.to(DEV))
+    assert rel_err(outL, refL) <= TOL and rel_err(outR, refR) <= TOL
+    # canonical site tensors reproduce the FSM pattern: identity in -> identity out.  In the reference's FSM layout
+    # (finite_state_machine.py:662-700) the LAST MPO state is "nothing has happened yet" (identity channel of L) and
+    # state 0 is "all terms completed" (identity channel of R).
+    Q, _ = torch.linalg.qr(randn((chi * 2, chip), dtype, 35))
+    Aiso = Q.reshape(chi, 2, chip)
+    L4 = _with_identity(randn((5, chi, chi), dtype, 36), 4)
+    outL = qsb.LeftEnvUpdate()(_lib.tag_identity(L4.to(DEV)), M.to(DEV), Aiso.to(DEV))
+    assert rel_err(outL, orc.left_env_update(L4, M, Aiso)) <= TOL
+    assert _lib.identity_of(outL)[0] == 4
+    Biso = Q.T.reshape(chip, 2, chi) if not dtype.is_complex else Q.conj().T.reshape(chip, 2, chi)
+    R0 = _with_identity(randn((5, chi, chi), dtype, 37), 0)
+    outR = qsb.RightEnvUpdate()(M.to(DEV), _lib.tag_identity(R0.to(DEV)), Biso.to(DEV))
+    assert rel_err(outR, orc.right_env_update(M, R0, Biso)) <= TOL
+    assert _lib.identity_of(outR)[0] == 0
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.complex128])
+@pytest.mark.parametrize("shape", [(1, 256, 128, 64), (2, 130, 70, 33), (1, 1024, 1024, 520)])
+def test_gemm_accumulate(dtype, shape):
+    Z, M, N, K = shape
+    A, B, C0 = randn((Z, M, K), dtype, 41), randn((Z, K, N), dtype, 42), randn((Z, M, N), dtype, 43)
+    out = C0.to(DEV).clone()
+    _lib.gemm(A.to(DEV), B.to(DEV), out=out, accumulate=True)
+    assert rel_err(out, C0 + torch.matmul(A, B)) <= TOL
+    out = C0.to(DEV).clone()
+    _lib.gemm(A.to(DEV), B.to(DEV), out=out)
+    assert rel_err(out, torch.matmul(A, B)) <= TOL
+
+
+def test_dmrg_sweep_uses_identity_channels():
+    """Inside a real sweep the environments of an FSM MPO carry identity channels and the kernels use them: the
+    energies still match the reference's golden run to 1e-10 (test_dmrg_matches_reference_per_update covers that);
+    here: the tags are what the FSM structure predicts."""
+    import io, contextlib
+    dt = torch.float64
+    mpo = golden_mpo("heis_f64_L20", dt, DEV)
+    with contextlib.redirect_stdout(io.StringIO()):
+        mps = qsb.MPS(20, 2, 32, "cpu", dt, 1).to(DEV)
+        env = qsb.EnvironmentManager(mpo, DEV, dt)
+        for p in range(19, 0, -1):
+            env.update_R(p, mps.B[p])
+    for p in range(1, 20):
+        assert _lib.identity_of(env.get_R(p))[0] == 0, p            # the FSM's "all terms completed" state
+    for p in range(0, 19):                                          # left-canonical tensors from a QR sweep
+        l, d, r = mps.B[p].shape
+        Q, Rf = torch.linalg.qr((mps.B[p] if p == 0 else torch.tensordot(Rf, mps.B[p], dims=([1], [0]))).reshape(l * d, r))
+        env.update_L(p, Q.reshape(l, d, Q.shape[1]))
+        assert _lib.identity_of(env.get_L(p + 1))[0] == mpo[p].shape[1] - 1, p

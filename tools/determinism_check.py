@@ -1,0 +1,167 @@
+#!/usr/bin/env python3
+"""Which operation makes a seeded GPU sweep non-repeatable?  (three runs of the seeded C3
+sweep gave three end-of-sweep energies, 2e-6 apart.)
+
+Part 1 runs every building block twice on identical inputs and compares the results BITWISE.
+Part 2 runs the same short DMRG twice while hashing every intermediate of every bond step (theta, Lanczos vector,
+U / S / Vh of the split, the new environment) and reports the first quantity that differs.
+
+    python tools/determinism_check.py [--chi 512] [--L 16]          (one GPU; prints JSON lines)
+"""
+import argparse
+import contextlib
+import hashlib
+import io
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import quantum_simulation_b200 as qsb           # noqa: E402
+from quantum_simulation_b200 import svd as qsvd  # noqa: E402
+from quantum_simulation_b200 import dmrg as qdmrg  # noqa: E402
+
+DEV = "cuda"
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def mpo(key, dtype):
+    z = np.load(os.path.join(ROOT, "tests", "golden", "mpo.npz"))
+    return [torch.from_numpy(z[f"{key}/t{int(u)}"]).to(dtype).contiguous().to(DEV) for u in z[f"{key}/index"]]
+
+
+def h(t):
+    return hashlib.sha1(t.detach().contiguous().cpu().numpy().tobytes()).hexdigest()[:12]
+
+
+def twice(name, fn, reps=3):
+    outs = []
+    for _ in range(reps):
+        r = fn()
+        r = r if isinstance(r, (tuple, list)) else (r,)
+        outs.append([h(x) for x in r])
+    same = all(o == outs[0] for o in outs)
+    print(json.dumps({"op": name, "bitwise_repeatable": same, "hashes": outs if not same else outs[0]}), flush=True)
+    return same
+
+
+def part1(chi):
+    dt = torch.float64
+    g = torch.Generator(device=DEV).manual_seed(5)
+    n = 2 * chi
+    a = torch.randn(n, n, dtype=dt, device=DEV, generator=g)
+    # spectrum like a DMRG theta: fast decay, many near-null directions
+    U0, _ = torch.linalg.qr(a)
+    s = torch.exp(-torch.arange(n, dtype=dt, device=DEV) * (30.0 / n))
+    theta = (U0 * s) @ torch.linalg.qr(a.T)[0]
+    G = theta @ theta.T
+    twice("torch.matmul (cuBLAS) Gram", lambda: theta @ theta.T)
+    twice("torch.linalg.eigh (cuSOLVER syevd)", lambda: torch.linalg.eigh(G))
+    twice("torch.linalg.qr tall (geqrf+orgqr)", lambda: torch.linalg.qr(theta[:, :chi]))
+    twice("torch.linalg.svd small 64x64 (default driver)", lambda: torch.linalg.svd(theta[:64, :64].contiguous()))
+    twice("torch.linalg.svd 512x512 (default driver)", lambda: torch.linalg.svd(theta[:512, :512].contiguous()))
+    twice("torch.linalg.cholesky", lambda: torch.linalg.cholesky(G + torch.eye(n, dtype=dt, device=DEV)))
+    twice("svd.two_site_split (gram path)", lambda: qsvd.two_site_split(theta, chi, 0.0)[:3])
+    twice("qsb gemm core", lambda: qsb._lib.gemm(theta, theta.T))
+    Ms = mpo("heis_f64_L20", dt)
+    L = torch.randn(5, chi, chi, dtype=dt, device=DEV, generator=g)
+    R = torch.randn(5, chi, chi, dtype=dt, device=DEV, generator=g)
+    L = L + L.transpose(1, 2)
+    R = R + R.transpose(1, 2)
+    psi = torch.randn(chi * 4 * chi, dtype=dt, device=DEV, generator=g)
+    op = qsb.ApplyMPO()
+    twice("qsb heff_apply", lambda: op(psi, L, Ms[9], Ms[10], R).clone())
+    A = torch.randn(chi, 2, chi, dtype=dt, device=DEV, generator=g)
+    twice("qsb env_left", lambda: qsb.LeftEnvUpdate()(L, Ms[9], A))
+    twice("qsb env_right", lambda: qsb.RightEnvUpdate()(Ms[9], R, A))
+    twice("qsb lanczos_ground_state",
+          lambda: qsb.lanczos_ground_state(psi, op, (L, Ms[9], Ms[10], R), num_restarts=2, krylov_dim=4)[0].clone())
+    twice("MPS built on the GPU (torch.rand + QR sweep), seed 1",
+          lambda: [t.detach() for t in quiet(qsb.MPS, 12, 2, chi, DEV, dt, 1).B])
+
+
+class Tap:
+    """Records a hash of every intermediate of every bond step of one DMRG run."""
+
+    def __init__(self):
+        self.log = []
+
+    def install(self):
+        tap = self
+        self._split = qdmrg.two_site_split
+        self._lan = qdmrg.lanczos_ground_state
+        self._mm = qdmrg._matmul2d
+        self._upL = qdmrg.EnvironmentManager.update_L
+        self._upR = qdmrg.EnvironmentManager.update_R
+
+        def split(theta, *a, **k):
+            tap.log.append(("split_in", h(theta)))
+            U, S, Vh, keep = tap._split(theta, *a, **k)
+            tap.log += [("U", h(U)), ("S", h(S)), ("Vh", h(Vh))]
+            return U, S, Vh, keep
+
+        def lan(x0, *a, **k):
+            tap.log.append(("theta0", h(x0)))
+            v, e = tap._lan(x0, *a, **k)
+            tap.log.append(("lanczos_vec", h(v)))
+            return v, e
+
+        def upL(self_, p, A):
+            tap._upL(self_, p, A)
+            tap.log.append(("envL", h(self_.L_cache[p + 1])))
+
+        def upR(self_, p, B):
+            tap._upR(self_, p, B)
+            tap.log.append(("envR", h(self_.R_cache[p])))
+
+        qdmrg.two_site_split, qdmrg.lanczos_ground_state = split, lan
+        qdmrg.EnvironmentManager.update_L, qdmrg.EnvironmentManager.update_R = upL, upR
+
+    def remove(self):
+        qdmrg.two_site_split, qdmrg.lanczos_ground_state = self._split, self._lan
+        qdmrg.EnvironmentManager.update_L, qdmrg.EnvironmentManager.update_R = self._upL, self._upR
+
+
+def part2(chi, L, mps_device):
+    dt = torch.float64
+    Ms = mpo("heis_f64_L100", dt)
+    Ms = Ms[:L // 2] + Ms[-(L - L // 2):]
+    runs = []
+    for _ in range(2):
+        tap = Tap()
+        tap.install()
+        try:
+            mps = quiet(qsb.MPS, L, 2, chi, mps_device, dt, 1).to(DEV)
+            sw = qsb.Sweeps(1)
+            sw.set_schedule(maxdim=[chi], cutoff=[0.0], krylov_dim=[4], noise=[0.0])
+            dm = quiet(qsb.DMRG, mps, Ms, device=DEV, dtype=dt)
+            E, _ = quiet(dm, sw, dispon=0, maxit=2)
+        finally:
+            tap.remove()
+        runs.append((tap.log, np.array(E)))
+    (la, Ea), (lb, Eb) = runs
+    first = next((i for i, (x, y) in enumerate(zip(la, lb)) if x != y), None)
+    rel = np.abs(Ea - Eb) / np.abs(Ea)
+    print(json.dumps({"dmrg_twice": f"Heisenberg L={L} chi={chi} f64, 1 sweep, MPS built on {mps_device}",
+                      "records": len(la), "first_differing_record": None if first is None else [first, la[first][0]],
+                      "context": None if first is None else [r[0] for r in la[max(0, first - 3): first + 2]],
+                      "energies_bitwise_equal": bool(np.array_equal(Ea, Eb)), "max_rel_energy_dev": float(rel.max()),
+                      "end_of_sweep": [float(Ea[-1]), float(Eb[-1])]}), flush=True)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--chi", type=int, default=512)
+    ap.add_argument("--L", type=int, default=16)
+    args = ap.parse_args()
+    part1(args.chi)
+    part2(min(args.chi, 256), args.L, "cpu")
+    part2(min(args.chi, 256), args.L, DEV)
