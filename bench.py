@@ -211,6 +211,26 @@ def dist_setup(n):
 # ----------------------------------------------------------------------------------------------
 # reference arm: the oracle (torch-CPU restatement of the reference's ncon path) on the host cores
 # ----------------------------------------------------------------------------------------------
+def reference_apply_mpo():
+    """(callable, kind): the UNMODIFIED reference's ``ApplyMPO('ncon')`` when it has been staged under baseline/_ref
+    (baseline/stage_reference.py; kind "reference"), else the oracle port of the same tensordot chain (kind "port")."""
+    try:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("_stage_reference", os.path.join(ROOT, "baseline", "stage_reference.py"))
+        st = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(st)
+        import contextlib
+        import io
+        with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+            st.import_reference()
+            from quantum_simulation.dmrg import ApplyMPO
+        mod = ApplyMPO("ncon")
+        return (lambda psi, L, M1, M2, R, out=None: mod(psi, L, M1, M2, R, out=out)), "reference"
+    except Exception:
+        from oracle import dmrg_oracle as orc
+        return orc.apply_mpo, "port"
+
+
 def cpu_matvec_time(chi, dtype, reps, rows=None, threads=None):
     from oracle import dmrg_oracle as orc
     threads = threads or os.cpu_count() or 1
@@ -218,12 +238,13 @@ def cpu_matvec_time(chi, dtype, reps, rows=None, threads=None):
     L, M1, M2, R, theta = make_inputs(chi, dtype, "cpu", rows=rows)
     flops = orc.matvec_flops(L, M1, M2, R)
     out = torch.empty(L.shape[1] * M1.shape[2] * M2.shape[2] * R.shape[1], dtype=dtype)
+    apply_mpo, kind = reference_apply_mpo()
     ts = []
     for _ in range(reps):
         t0 = time.perf_counter()
-        orc.apply_mpo(theta, L, M1, M2, R, out=out)
+        apply_mpo(theta, L, M1, M2, R, out=out)
         ts.append(time.perf_counter() - t0)
-    return ts, flops, threads
+    return ts, flops, threads, kind
 
 
 def run_reference(args):
@@ -233,23 +254,26 @@ def run_reference(args):
     dtype = torch.float64 if args.dtype == "f64" else torch.complex128
     cores = os.cpu_count() or 1
     # one full-size matvec decides the bounded sample: a block of `rows` left-bond rows of the same problem
-    ts, flops_full, threads = cpu_matvec_time(args.chi, dtype, 1)
+    ts, flops_full, threads, kind = cpu_matvec_time(args.chi, dtype, 1)
     budget = 200.0
     total_steps = args.steps + args.warmup
     frac = min(1.0, budget / max(ts[0] * total_steps, 1e-9))
     rows = max(64, int(args.chi * frac) // 64 * 64) if frac < 1.0 else args.chi
     rows = min(rows, args.chi)
-    ts, flops, _ = cpu_matvec_time(args.chi, dtype, total_steps, rows=rows)
+    ts, flops, _, kind = cpu_matvec_time(args.chi, dtype, total_steps, rows=rows)
     timed = ts[args.warmup:]
     sec = sum(timed) / len(timed)
     val = flops / sec / 1e9
     sample = (f"rows [0,{rows}) of the left bond (of {args.chi}) of the same chi={args.chi} matvec per step, "
-              f"{len(timed)} timed steps, oracle ncon-order tensordots on torch CPU ({torch.__config__.parallel_info().splitlines()[0]})")
+              f"{len(timed)} timed steps, "
+              + ("the unmodified reference's ApplyMPO('ncon') (baseline/_ref)" if kind == "reference" else
+                 "oracle port of the reference's ncon-order tensordots")
+              + f" on torch CPU ({torch.__config__.parallel_info().splitlines()[0]})")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": workload_config(args, args.gpus),
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -649,11 +673,13 @@ def extras(args, qsb, _lib, dev, dtype, L, M1, M2, R, theta, peak_tf):
     cores = os.cpu_count() or 1
     try:
         rows = chi if chi <= 1024 else max(256, chi // 4)
-        ts, fl, threads = cpu_matvec_time(chi, dtype, 3, rows=rows)
+        ts, fl, threads, kind = cpu_matvec_time(chi, dtype, 3, rows=rows)
         sec = min(ts[1:])
-        out["cpu_baseline"] = {"value": fl / sec / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
+        out["cpu_baseline"] = {"value": fl / sec / 1e9, "unit": UNIT, "cores": threads, "kind": kind,
                                "sample": f"rows [0,{rows}) of {chi} of the same chi={chi} matvec, best of 2 after 1 "
-                                         f"warm-up, torch-CPU oracle (ncon order), {threads} threads",
+                                         f"warm-up, " + ("the unmodified reference's ApplyMPO('ncon') from baseline/_ref"
+                                                         if kind == "reference" else "torch-CPU oracle (ncon order)")
+                                         + f", {threads} threads",
                                "ms_sample": sec * 1e3}
     except Exception as ex:
         out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": cores, "kind": "port", "sample": repr(ex)[:200]}
