@@ -493,10 +493,10 @@ __global__ void __launch_bounds__(256) identity_dev_kernel(const char* env, long
         } else {
             dv = fabs(reinterpret_cast<const double*>(env)[o] - want);
         }
-        if (!(dv <= m)) m = dv;                          // NaN propagates as "not an identity"
+        if (dv > m || dv != dv) m = dv;                  // a NaN sticks: "not an identity"
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_xor_sync(0xffffffffu, m, o); if (!(t <= m)) m = t; }
+    for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_xor_sync(0xffffffffu, m, o); if (t > m || t != t) m = t; }
     if ((threadIdx.x & 31) == 0) {
         if (m != m) m = 1e300;
         atomicMax(maxdev + w, (unsigned long long)__double_as_longlong(m));    // non-negative doubles order as integers
