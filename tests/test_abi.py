@@ -210,3 +210,32 @@ def test_mps_constructor_and_position_match_reference_fixture():
             assert np.allclose(m.B[p].detach().numpy(), z[f"{tag}/B{p}"], rtol=0, atol=1e-15)
         for p in range(N + 1):
             assert np.allclose(m.sWeight[p].detach().numpy(), z[f"{tag}/s{p}"], rtol=0, atol=1e-15)
+
+
+def test_documented_binding_matches_the_header():
+    """INTEGRATION.md's stub stopped short of the real struct.  Now: the standalone binding
+    (integration/qsb200_binding.py), the struct text quoted in INTEGRATION.md, this package's own mirror and the
+    compiled library all agree, field for field and byte for byte."""
+    import ctypes as C
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_qsb200_binding", os.path.join(ROOT, "integration", "qsb200_binding.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    lib = b.load()                                            # asserts sizeof against qsb_sizeof_*()
+    for mine, theirs in ((_lib.HeffDesc, b.HeffDesc), (_lib.EnvDesc, b.EnvDesc)):
+        assert [(n, C.sizeof(t)) for n, t in mine._fields_] == [(n, C.sizeof(t)) for n, t in theirs._fields_]
+        assert C.sizeof(mine) == C.sizeof(theirs)
+    assert lib.qsb_sizeof_heff_desc() == C.sizeof(b.HeffDesc)
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    hdr = open(os.path.join(ROOT, "include", "qsb200.h")).read()
+    for st, cname in ((b.HeffDesc, "qsb_heff_desc"), (b.EnvDesc, "qsb_env_desc")):
+        names = [n for n, _ in st._fields_]
+        doc_names = re.findall(r'\("(\w+)", C\.', doc[doc.index(f"== {cname}"):].split("]\n\n")[0])
+        assert doc_names == names, f"INTEGRATION.md stub of {cname} drifted"
+        body = hdr[:hdr.index(f"}} {cname};")]
+        body = body[body.rindex("typedef struct {"):]
+        at = 0                                                # every field appears in the header, in this order
+        for n in names:
+            m = re.compile(rf"\b{n}\b").search(body, at)
+            assert m is not None, f"{cname}.{n} missing from (or out of order in) include/qsb200.h"
+            at = m.end()
