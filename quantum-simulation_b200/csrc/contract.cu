@@ -489,7 +489,8 @@ __global__ void __launch_bounds__(256) identity_dev_kernel(const char* env, long
         double dv;
         if constexpr (CPLX) {
             const double2 v = reinterpret_cast<const double2*>(env)[o];
-            dv = fmax(fabs(v.x - want), fabs(v.y));
+            const double a = fabs(v.x - want), b = fabs(v.y);
+            dv = (a > b || a != a) ? a : b;              // (fmax would drop a NaN)
         } else {
             dv = fabs(reinterpret_cast<const double*>(env)[o] - want);
         }

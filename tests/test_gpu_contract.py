@@ -509,10 +509,12 @@ def test_dmrg_sweep_uses_identity_channels():
         env = qsb.EnvironmentManager(mpo, DEV, dt)
         for p in range(19, 0, -1):
             env.update_R(p, mps.B[p])
-    for p in range(1, 20):
+    for p in range(2, 20):
         assert _lib.identity_of(env.get_R(p))[0] == 0, p            # the FSM's "all terms completed" state
+    assert _lib.identity_of(env.get_R(1))[0] == -1                  # bond 0|1 (W = 4): no term can be complete yet
     for p in range(0, 19):                                          # left-canonical tensors from a QR sweep
         l, d, r = mps.B[p].shape
         Q, Rf = torch.linalg.qr((mps.B[p] if p == 0 else torch.tensordot(Rf, mps.B[p], dims=([1], [0]))).reshape(l * d, r))
         env.update_L(p, Q.reshape(l, d, Q.shape[1]))
-        assert _lib.identity_of(env.get_L(p + 1))[0] == mpo[p].shape[1] - 1, p
+        want = mpo[p].shape[1] - 1 if p < 18 else -1                # bond 18|19 (W = 4): every term has started
+        assert _lib.identity_of(env.get_L(p + 1))[0] == want, p

@@ -88,6 +88,34 @@ def part1(chi):
           lambda: [t.detach() for t in quiet(qsb.MPS, 12, 2, chi, DEV, dt, 1).B])
 
 
+def part_big(n=4096):
+    """The library calls of a chi = n/2 bond step at full size: repeatable inside a process?  (Run the tool twice and
+    diff the logs for the cross-process answer: the hashes are printed.)"""
+    dt = torch.float64
+    g = torch.Generator(device=DEV).manual_seed(11)
+    a = torch.randn(n, n, dtype=dt, device=DEV, generator=g)
+    U0, _ = torch.linalg.qr(a)
+    s = torch.exp(-torch.arange(n, dtype=dt, device=DEV) * (30.0 / n))
+    theta = (U0 * s) @ torch.linalg.qr(a.T)[0]
+    G = qsb._lib.gemm(theta, theta.T)
+    G = 0.5 * (G + G.T)
+    k = n // 2
+    twice(f"BIG qsb gemm Gram {n}", lambda: qsb._lib.gemm(theta, theta.T), 2)
+    twice(f"BIG torch.matmul {n}", lambda: theta @ theta.T, 2)
+    twice(f"BIG torch.linalg.eigh {n}", lambda: torch.linalg.eigh(G), 2)
+    twice(f"BIG torch.linalg.qr {n}x{k}", lambda: torch.linalg.qr(theta[:, :k]), 2)
+    Gk = G[:k, :k] + torch.eye(k, dtype=dt, device=DEV)
+    twice(f"BIG cholesky_ex {k}", lambda: torch.linalg.cholesky_ex(Gk)[0], 2)
+    Lc = torch.linalg.cholesky(Gk)
+    twice(f"BIG solve_triangular {k}x{n}", lambda: torch.linalg.solve_triangular(Lc, theta[:k], upper=False), 2)
+    twice(f"BIG two_site_split {n}", lambda: qsvd.two_site_split(theta, k, 0.0)[:3], 2)
+    twice("BIG einsum lsc,ck->lsk", lambda: torch.einsum("lsc,ck->lsk", theta.view(k, 2, n), a[:, :k].contiguous()), 2)
+    twice(f"BIG MPS built on the GPU, L=14 chi={k // 2}, seed 1",
+          lambda: [t.detach() for t in quiet(qsb.MPS, 14, 2, k // 2, DEV, dt, 1).B], 2)
+    twice("BIG torch.rand with a device generator",
+          lambda: torch.rand(1000, 1000, generator=torch.Generator(device=DEV).manual_seed(1), device=DEV, dtype=dt), 2)
+
+
 class Tap:
     """Records a hash of every intermediate of every bond step of one DMRG run."""
 
@@ -161,7 +189,11 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--chi", type=int, default=512)
     ap.add_argument("--L", type=int, default=16)
+    ap.add_argument("--big", action="store_true")
     args = ap.parse_args()
+    if args.big:
+        part_big()
+        sys.exit(0)
     part1(args.chi)
     part2(min(args.chi, 256), args.L, "cpu")
     part2(min(args.chi, 256), args.L, DEV)
