@@ -502,10 +502,130 @@ def run_ours(args):
         line.update(extras(args, qsb, _lib, dev, dtype, L, M1, M2, R, theta, peak_tf))
         if line.get("cublas_dgemm_8192_tflops"):
             line["roofline_frac_vs_cublas_dgemm"] = roofline["achieved"] / line["cublas_dgemm_8192_tflops"]
+    if world > 1 and not args.no_extras:
+        # every rank takes part (collectives inside); rank 0 keeps the numbers
+        del L, R, theta, out, fused
+        _lib.release_workspaces()
+        torch.cuda.empty_cache()
+        if args.model == "heis" and not args.no_sweep:
+            line["sweep"] = sharded_sweep_leg(args, qsb, dev, dtype, rank, world)
+        if world >= 8 and args.model == "heis" and args.chi == 2048:
+            line["large"] = large_configs_leg(args, qsb, _lib, dev, rank, world, local, peak_tf)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def sharded_sweep_leg(args, qsb, dev, dtype, rank, world):
+    """N > 1, the other half of BASELINE.json's metric: one FULL two-site DMRG sweep of the same config through
+    ShardedDMRG (row-sharded environments and Lanczos, fused exchange), timed like the N = 1 'sweep' leg."""
+    import contextlib
+    import io
+    import torch.distributed as dist
+    from quantum_simulation_b200.parallel import ShardedDMRG
+    try:
+        chi, Lsites = args.chi, 100
+        key = "heis_f64_L100" if dtype == torch.float64 else "heis_c128_L100"
+        mpo = [m.to(dev) for m in load_mpo(key, dtype)]
+
+        def build(L, c):
+            with contextlib.redirect_stdout(io.StringIO()):
+                m = qsb.MPS(L, 2, c, dev, dtype, seed=1)
+            for plist in (m.A, m.B, m.sWeight):                    # identical tensors on every rank (rank 0's)
+                for t in plist:
+                    dist.broadcast(torch.view_as_real(t.data) if t.is_complex() else t.data, src=0)
+            return m
+
+        def sched(c):
+            sw = qsb.Sweeps(1)
+            sw.set_schedule(maxdim=[c], cutoff=[0.0], krylov_dim=[4], noise=[0.0])
+            return sw
+        # warm-up on a short chain: NCCL communicators, symmetric-memory machinery, cuSOLVER handles
+        small = [mpo[0], mpo[1]] + [mpo[50]] * 12 + [mpo[-2], mpo[-1]]
+        ShardedDMRG(build(16, 128), small, device=dev, dtype=dtype)(sched(128), dispon=0)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        mps = build(Lsites, chi)
+        torch.cuda.synchronize()
+        t_init = time.perf_counter() - t0
+        dm = ShardedDMRG(mps, mpo, device=dev, dtype=dtype)
+        dm.profile = False
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        Es, _ = dm(sched(chi), dispon=0, maxit=2)
+        torch.cuda.synchronize()
+        dist.barrier()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        bd = dm.history["bond_dims"]
+        res = {"seconds": float(t.item()), "bond_updates": len(Es), "updates_at_full_chi": int(sum(b == chi for b in bd)),
+               "mps_init_on_gpu_s": t_init, "energy_end_of_sweep": float(Es[-1]), "comm": dm.comm,
+               "peak_memory_gb": torch.cuda.max_memory_allocated() / 1e9,
+               "what": f"one full two-site DMRG sweep through ShardedDMRG on {world} GPUs, Heisenberg L={Lsites}, chi={chi}, "
+                       f"{args.dtype}, krylov_dim=4, maxit=2, cutoff=0, the same random right-canonical start as the "
+                       "N=1 'sweep' leg; wall clock, device synchronise + barrier on both sides, max over ranks"}
+        del dm, mps
+        qsb.clear_workspaces()
+        torch.cuda.empty_cache()
+        return res
+    except Exception as ex:
+        return {"error": repr(ex)[:300]}
+
+
+def large_configs_leg(args, qsb, _lib, dev, rank, world, local, peak_tf):
+    """north_star: "scaling to 8 GPUs at chi >= 4096" -- BASELINE configs 4 (J1-J2 cylinder, MPO bond ~30, float64) and
+    5 (Fermi-Hubbard via Jordan-Wigner, d = 4, complex128) at chi = 4096, the sharded matvec with the fused exchange."""
+    global _MODEL
+    import torch.distributed as dist
+    from quantum_simulation_b200.parallel import FusedShardedApplyMPO
+    out = {}
+    saved = _MODEL
+    for model, dts in (("j1j2", "f64"), ("hubbard", "c128")):
+        try:
+            _MODEL = model
+            dtype = torch.float64 if dts == "f64" else torch.complex128
+            chi = 4096
+            rows = chi // world
+            L, M1, M2, R, theta = make_inputs(chi, dtype, dev, rows=rows, row0=rank * rows)
+            _lib.tag_identity(L, rank * rows)
+            _lib.tag_identity(R)
+            ident = (_lib.identity_of(L)[0], _lib.identity_of(R)[0], rank * rows)
+            shard = theta.view(world, -1)[rank].clone()
+            del theta
+            op = FusedShardedApplyMPO(chi, M1.shape[3] * M2.shape[3] * chi, dtype, dev)
+            res = torch.empty(rows * M1.shape[2] * M2.shape[2] * chi, dtype=dtype, device=dev)
+            for _ in range(2):
+                op(shard, L, M1, M2, R, out=res)
+            torch.cuda.synchronize()
+            sampler = ClockSampler(local)
+            if rank == 0:
+                sampler.start()
+            dist.barrier()
+            K = 5
+            sec = time_region(lambda: op(shard, L, M1, M2, R, out=res), K)
+            dist.barrier()
+            clocks = sampler.stop() if rank == 0 else None
+            t = torch.tensor([sec], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sec = float(t.item()) / K
+            dense = _lib.heff_flops(torch.empty(0, dtype=dtype, device=dev), L, M1, M2, R) * world
+            execd = _lib.heff_flops_executed(torch.empty(0, dtype=dtype, device=dev), L, M1, M2, R, ident) * world
+            kf, kc, site, desc = MODELS[model]
+            out[model] = {"workload": f"{desc}, chi={chi}, bulk bond {site}|{site + 1}, MPO bonds {M1.shape[0]}-"
+                                      f"{M1.shape[1]}-{M2.shape[1]}, d={M1.shape[2]}, {dts}", "n_gpus": world,
+                          "ms_per_matvec": sec * 1e3, "tflops_effective": dense / sec / 1e12,
+                          "tflops_executed": execd / sec / 1e12,
+                          "frac_of_fp64_tensor_peak_per_gpu": execd / sec / 1e12 / world / peak_tf if peak_tf else None,
+                          "identity_channels": {"L": ident[0], "R": ident[1]}, "steps": K, "clocks": clocks}
+            del L, R, shard, res, op
+            _lib.release_workspaces()
+            torch.cuda.empty_cache()
+        except Exception as ex:
+            out[model] = {"error": repr(ex)[:300]}
+    _MODEL = saved
+    return out
 
 
 def extras(args, qsb, _lib, dev, dtype, L, M1, M2, R, theta, peak_tf):

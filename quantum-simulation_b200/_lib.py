@@ -201,17 +201,22 @@ def _resolved(t: torch.Tensor) -> torch.Tensor:
 
 
 # ---------------------------------------------------------------------------------------------
-# per-device workspaces (grown on demand, reused by every call on that device)
+# workspaces: one per (device, stream), grown on demand, reused by every call on that stream.  Calls on one stream are
+# ordered, so they can share scratch; calls on different streams of a device get their own (re-entrant per
+# (device, stream)).  The C library keeps its stream-K scratch by the same key.
 # ---------------------------------------------------------------------------------------------
-_workspaces: Dict[torch.device, torch.Tensor] = {}
+_workspaces: Dict[tuple, torch.Tensor] = {}
 
 
 def workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
-    ws = _workspaces.get(dev)
-    if ws is None or ws.numel() < nbytes:
-        _workspaces[dev] = None  # release before growing
-        ws = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=dev)
-        _workspaces[dev] = ws
+    with torch.cuda.device(dev):
+        key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device(),
+               torch.cuda.current_stream().cuda_stream)
+        ws = _workspaces.get(key)
+        if ws is None or ws.numel() < nbytes:
+            _workspaces[key] = None  # release before growing (the allocator keeps the block for THIS stream's later use)
+            ws = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=dev)
+            _workspaces[key] = ws
     return ws
 
 

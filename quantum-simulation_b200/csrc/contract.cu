@@ -296,9 +296,10 @@ static int heff_check(const qsb_heff_desc* d) {
     return QSB_OK;
 }
 
-// profiling hook (qsb_heff_set_stage_events): events recorded at the stage boundaries of heff_apply
-static cudaEvent_t g_stage_events[4];
-static int g_stage_event_count = 0;
+// profiling hook (qsb_heff_set_stage_events): events recorded at the stage boundaries of heff_apply; per host thread,
+// so a thread that profiles its own calls does not make another thread's calls record into its events
+static thread_local cudaEvent_t g_stage_events[4];
+static thread_local int g_stage_event_count = 0;
 static inline void stage_mark(int i, cudaStream_t s) {
     if (g_stage_event_count == 4) cudaEventRecord(g_stage_events[i], s);
 }

@@ -16,6 +16,8 @@
 // * Out-of-range k (and rows of KC operands) are zero-filled by the TMA, so ragged extents need no copies.
 #include "common.cuh"
 #include <mutex>
+#include <map>
+#include <utility>
 #include <cstdlib>
 
 namespace qsb {
@@ -546,15 +548,18 @@ static bool make_map(CUtensorMap* map, const Operand& o, bool cplx, bool kc, int
     return r == CUDA_SUCCESS;
 }
 
-// stream-K scratch, one per device, owned by the library (kernels of one device must not run concurrently on
-// several streams; the DMRG loop is single-stream like the reference)
+// stream-K scratch (partial tiles + flags + epoch), owned by the library: one per (device, stream), so GEMMs issued
+// on different streams of one device never share partial-tile storage (re-entrant per (device, stream)).
+// Launches on ONE stream are ordered, which is all a scratch needs.  Entries live for the life of the process.
 struct SkScratch { double* partial = nullptr; int* flags = nullptr; int sms = 0; int epoch = 0; };
-static SkScratch g_sk[16];
+static std::mutex g_sk_mutex;
+static std::map<std::pair<int, cudaStream_t>, SkScratch> g_sk;
 
-static int sk_scratch(SkScratch** out) {
+static int sk_scratch(SkScratch** out, cudaStream_t stream) {
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return QSB_ERR_DEVICE;
-    SkScratch& s = g_sk[dev];
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) return QSB_ERR_DEVICE;
+    std::lock_guard<std::mutex> lock(g_sk_mutex);
+    SkScratch& s = g_sk[std::make_pair(dev, stream)];
     if (!s.partial) {
         int rc = check_cuda(cudaDeviceGetAttribute(&s.sms, cudaDevAttrMultiProcessorCount, dev));
         if (rc) return rc;
@@ -583,7 +588,7 @@ static int launch_tma_g(const CUtensorMap& ma, const CUtensorMap& mb, const TArg
         configured[dev] = true;
     }
     SkScratch* sc = nullptr;
-    int rc = sk_scratch(&sc);
+    int rc = sk_scratch(&sc, stream);
     if (rc) return rc;
     const long long tiles = (long long)t.tiles_m * t.tiles_n * Z;
     if (tiles > 2147483647LL) return QSB_ERR_SHAPE;

@@ -183,12 +183,13 @@ class ApplyMPO(_BaseContractModule):
         if out_host.numel() != n_out or out_host.dtype != dt or out_host.device.type != "cpu" \
                 or not out_host.is_pinned() or not out_host.is_contiguous():
             raise ValueError("[ApplyMPO] out shape/device/dtype mismatch.")
-        pipe = ApplyMPO._host_pipes.get(dev)
+        pipe_key = (dev, torch.cuda.current_stream(dev).cuda_stream)     # one pipeline per (device, launching stream)
+        pipe = ApplyMPO._host_pipes.get(pipe_key)
         if pipe is None:
             pipe = {"flags": torch.zeros(64, dtype=torch.int32, device=dev), "epoch": 0,
                     "h2d": torch.cuda.Stream(device=dev), "d2h": torch.cuda.Stream(device=dev), "theta": None,
                     "out": None}
-            ApplyMPO._host_pipes[dev] = pipe
+            ApplyMPO._host_pipes[pipe_key] = pipe
         for key, numel in (("theta", n_in), ("out", n_out)):
             buf = pipe[key]
             if buf is None or buf.numel() < numel or buf.dtype != dt:
@@ -262,7 +263,29 @@ class ApplyMPO(_BaseContractModule):
             pipe["last_mode"] = mode
             main.wait_stream(pipe["d2h"])                  # the result is on the host once `main` gets here
             main.wait_stream(pipe["h2d"])
+            pipe["done"] = torch.cuda.Event()
+            pipe["done"].record(main)
+        # CONTRACT: the copies are asynchronous.  `out_host` holds the result -- and `psi_host` may be
+        # overwritten -- only after the launching stream has reached this point: synchronise the stream (or the device),
+        # or call ApplyMPO.host_result_ready(device).synchronize().
         return out_host
+
+    @classmethod
+    def host_result_ready(cls, device=None) -> "torch.cuda.Event":
+        """Event recorded after the last download of the most recent host-resident call on the current stream."""
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        pipe = cls._host_pipes.get((dev, torch.cuda.current_stream(dev).cuda_stream))
+        if pipe is None or "done" not in pipe:
+            raise RuntimeError("no host-resident ApplyMPO call has been issued on this (device, stream)")
+        return pipe["done"]
+
+    @classmethod
+    def release_host_pipes(cls) -> None:
+        """Free the device staging buffers (2 n elements per (device, stream)) of the host-resident path."""
+        torch.cuda.synchronize()
+        cls._host_pipes.clear()
 
 
 class LeftEnvUpdate(_BaseContractModule):

@@ -79,7 +79,8 @@ _workspaces: Dict[tuple, _Workspace] = {}
 
 
 def _ensure_ws(n: int, k: int, device: torch.device, dtype: torch.dtype, vec) -> _Workspace:
-    key = (n, k, device.type, device.index, dtype, id(vec))
+    stream = torch.cuda.current_stream(device).cuda_stream if device.type == "cuda" else 0
+    key = (n, k, device.type, device.index, dtype, id(vec), stream)      # one workspace per (device, stream)
     ws = _workspaces.get(key)
     if ws is None:
         ws = _Workspace(n, k, device, dtype, vec)

@@ -39,7 +39,14 @@ def mpo(key, dtype):
 
 
 def h(t):
-    return hashlib.sha1(t.detach().contiguous().cpu().numpy().tobytes()).hexdigest()[:12]
+    """Bit-level fingerprint: SHA-1 of the bytes for small tensors; for large ones two wrap-around int64 sums over
+    the raw 64-bit words computed on the device (a full-size sweep hashes ~200 GB of intermediates)."""
+    t = t.detach().contiguous()
+    if t.numel() * t.element_size() > (1 << 22) and t.is_cuda and t.element_size() in (8, 16):
+        w = torch.view_as_real(t).reshape(-1).view(torch.int64) if t.is_complex() else t.reshape(-1).view(torch.int64)
+        idx = torch.arange(w.numel(), device=w.device, dtype=torch.int64)
+        return f"{int(w.sum().item()) & 0xffffffffffff:012x}{int((w * (2 * idx + 1)).sum().item()) & 0xffffff:06x}"
+    return hashlib.sha1(t.cpu().numpy().tobytes()).hexdigest()[:12]
 
 
 def twice(name, fn, reps=3):
@@ -178,8 +185,10 @@ def part2(chi, L, mps_device):
     (la, Ea), (lb, Eb) = runs
     first = next((i for i, (x, y) in enumerate(zip(la, lb)) if x != y), None)
     rel = np.abs(Ea - Eb) / np.abs(Ea)
+    digest = hashlib.sha1(repr(la).encode()).hexdigest()[:16]       # compare across PROCESSES by diffing two logs
     print(json.dumps({"dmrg_twice": f"Heisenberg L={L} chi={chi} f64, 1 sweep, MPS built on {mps_device}",
-                      "records": len(la), "first_differing_record": None if first is None else [first, la[first][0]],
+                      "records": len(la), "log_digest_run1": digest,
+                      "first_records": [list(r) for r in la[:6]], "first_differing_record": None if first is None else [first, la[first][0]],
                       "context": None if first is None else [r[0] for r in la[max(0, first - 3): first + 2]],
                       "energies_bitwise_equal": bool(np.array_equal(Ea, Eb)), "max_rel_energy_dev": float(rel.max()),
                       "end_of_sweep": [float(Ea[-1]), float(Eb[-1])]}), flush=True)
@@ -190,9 +199,14 @@ if __name__ == "__main__":
     ap.add_argument("--chi", type=int, default=512)
     ap.add_argument("--L", type=int, default=16)
     ap.add_argument("--big", action="store_true")
+    ap.add_argument("--sweep-only", action="store_true", help="only the twice-in-one-process DMRG with hashed intermediates")
     args = ap.parse_args()
     if args.big:
         part_big()
+        part2(args.chi, args.L, DEV)
+        sys.exit(0)
+    if args.sweep_only:
+        part2(args.chi, args.L, DEV)
         sys.exit(0)
     part1(args.chi)
     part2(min(args.chi, 256), args.L, "cpu")
