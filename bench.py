@@ -552,6 +552,7 @@ def sharded_sweep_leg(args, qsb, dev, dtype, rank, world):
         dm = ShardedDMRG(mps, mpo, device=dev, dtype=dtype)
         dm.profile = False
         dist.barrier()
+        torch.manual_seed(1)             # see the N = 1 'sweep' leg: the first Lanczos start comes from the global RNG
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         Es, _ = dm(sched(chi), dispon=0, maxit=2)
@@ -774,6 +775,10 @@ def extras(args, qsb, _lib, dev, dtype, L, M1, M2, R, theta, peak_tf):
                 sw.set_schedule(maxdim=[chi], cutoff=[0.0], krylov_dim=[4], noise=[0.0])
                 key = "heis_f64_L100" if dtype == torch.float64 else "heis_c128_L100"
                 dm = qsb.DMRG(mps, [m.to(dev) for m in load_mpo(key, dtype)], device=dev, dtype=dtype)
+                # At L=100, chi=2048 the reference's MPS constructor (and its mirror) yields a ZERO centre tensor (the
+                # carry's squared norm overflows), so the first Lanczos start vector is re-seeded from the GLOBAL RNG
+                # (lanczos_solver.py:150-153): seed it, or two runs differ by 2e-6 (r01's drift; tools/first_bond_diag.py)
+                torch.manual_seed(1)
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
                 Es, _ = dm(sw, dispon=0, maxit=2)
@@ -783,6 +788,8 @@ def extras(args, qsb, _lib, dev, dtype, L, M1, M2, R, theta, peak_tf):
             out["sweep"] = {"seconds": t_sweep, "bond_updates": len(Es), "updates_at_full_chi": int(sum(b == chi for b in bd)),
                             "mps_init_on_gpu_s": t_init, "energy_end_of_sweep": float(Es[-1]),
                             "peak_memory_gb": torch.cuda.max_memory_allocated() / 1e9,
+                            "rng": "torch.manual_seed(1) before the sweep (the zero centre tensor of the L=100/chi=2048 "
+                                   "start makes the first Lanczos start a global-RNG draw, as in the reference)",
                             "what": f"one full two-site DMRG sweep, Heisenberg L={Lsites}, chi={chi}, {args.dtype}, "
                                     "krylov_dim=4, maxit=2, cutoff=0, random right-canonical start; wall clock with a "
                                     "device synchronise on both sides"}

@@ -143,6 +143,24 @@ def load() -> C.CDLL:
     return lib
 
 
+class nvtx_range:
+    """NVTX range around a hot-path call (visible in nsys / ncu --nvtx), enabled with QSB200_NVTX=1: zero cost
+    otherwise.  Ranges: qsb.heff_apply, qsb.env_left / env_right, qsb.lanczos, qsb.two_site_split."""
+    enabled = os.environ.get("QSB200_NVTX", "0") not in ("", "0")
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        if nvtx_range.enabled:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if nvtx_range.enabled:
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
 def status_string(code: int) -> str:
     return load().qsb_status_string(int(code)).decode()
 
@@ -320,7 +338,7 @@ def _impl_heff_apply(psi, L, M1, M2, R, out, gate=None, ident=(-1, -1, 0)) -> No
     ws = workspace(dev, nb.value)
     d.workspace = ws.data_ptr()
     d.workspace_bytes = ws.numel()
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), nvtx_range("qsb.heff_apply"):
         check(lib.qsb_heff_apply(C.byref(d), _stream()), "ApplyMPO")
 
 
@@ -432,7 +450,7 @@ def _impl_env(env, M, site, out, left: bool, site_bra=None, ident: int = -1) -> 
     ws = workspace(dev, nb.value)
     d.workspace = ws.data_ptr()
     d.workspace_bytes = ws.numel()
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), nvtx_range("qsb.env_left" if left else "qsb.env_right"):
         check((lib.qsb_env_left if left else lib.qsb_env_right)(C.byref(d), _stream()),
               "LeftEnvUpdate" if left else "RightEnvUpdate")
 

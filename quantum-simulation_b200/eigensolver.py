@@ -218,5 +218,6 @@ def lanczos_ground_state(
     """
     if initial_vector.device.type != "cuda":
         raise RuntimeError("qsb200 lanczos_ground_state runs on CUDA tensors only (no CPU fallback)")
-    return _lanczos_impl(initial_vector, linear_operator, operator_args, num_restarts, krylov_dim, pro,
-                         pro_max_reorth, beta_tol, ritz_residual_tol)
+    with _lib.nvtx_range("qsb.lanczos"):
+        return _lanczos_impl(initial_vector, linear_operator, operator_args, num_restarts, krylov_dim, pro,
+                             pro_max_reorth, beta_tol, ritz_residual_tol)

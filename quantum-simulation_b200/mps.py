@@ -57,6 +57,17 @@ class MPS(nn.Module):
             sites[p], carry = _absorb_right_factor(sites[p])
             sites[p - 1] = torch.einsum("lsc,ck->lsk", sites[p - 1], carry)
         sites[0] = sites[0] / torch.linalg.norm(sites[0])
+        # Same arithmetic as the reference (mps.py:57-60) -- including its failure mode: the carry is never rescaled,
+        # uniform[0,1) sites have a rank-1 mean component of norm ~0.5*sqrt(l*d*r), so for long chains at large chi
+        # (L=100, chi=2048: ~1e280 at site 0) the SQUARED norm overflows, linalg.norm returns inf and site 0 becomes
+        # exactly zero.  DMRG still works -- the first Lanczos call re-seeds its zero start vector
+        # (lanczos_solver.py:150-153) -- but from the GLOBAL RNG, so such a run repeats only under torch.manual_seed.
+        if not bool(torch.isfinite(sites[0]).all()) or not bool(sites[0].any()):
+            import warnings
+            warnings.warn("MPS: the un-normalised canonicalisation carry over/underflowed (site 0 is zero or "
+                          "non-finite), exactly as in the reference at this size; the first DMRG update will start from "
+                          "a vector drawn from the global RNG -- call torch.manual_seed(...) for a repeatable run",
+                          RuntimeWarning, stacklevel=2)
         ones = [torch.ones(1, device=device, dtype=dtype) for _ in range(Nsites + 1)]
         self._A = nn.ParameterList(_frozen(t) for t in sites)
         self._B = nn.ParameterList(_frozen(t.clone()) for t in sites)

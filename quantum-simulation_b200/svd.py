@@ -119,6 +119,10 @@ def two_site_split(theta: torch.Tensor, maxdim: int, cutoff: float, *, fast_min:
     ``S_all`` is the full descending spectrum (the caller records the discarded weight from ``S_all[keep:]``)."""
     fm = FAST_MIN if fast_min is None else fast_min
     if min(theta.shape) >= fm:
+        if theta.is_cuda:
+            from ._lib import nvtx_range
+            with nvtx_range("qsb.two_site_split"):
+                return _gram_split(theta, maxdim, cutoff)
         return _gram_split(theta, maxdim, cutoff)
     U, S, Vh = torch.linalg.svd(theta, full_matrices=False)         # dmrg.py:685
     keep = _keep_from_spectrum(S, maxdim, cutoff)

@@ -165,7 +165,7 @@ class Tap:
         qdmrg.EnvironmentManager.update_L, qdmrg.EnvironmentManager.update_R = self._upL, self._upR
 
 
-def part2(chi, L, mps_device):
+def part2(chi, L, mps_device, seed_global=None):
     dt = torch.float64
     Ms = mpo("heis_f64_L100", dt)
     Ms = Ms[:L // 2] + Ms[-(L - L // 2):]
@@ -178,6 +178,8 @@ def part2(chi, L, mps_device):
             sw = qsb.Sweeps(1)
             sw.set_schedule(maxdim=[chi], cutoff=[0.0], krylov_dim=[4], noise=[0.0])
             dm = quiet(qsb.DMRG, mps, Ms, device=DEV, dtype=dt)
+            if seed_global is not None:
+                torch.manual_seed(seed_global)
             E, _ = quiet(dm, sw, dispon=0, maxit=2)
         finally:
             tap.remove()
@@ -186,7 +188,8 @@ def part2(chi, L, mps_device):
     first = next((i for i, (x, y) in enumerate(zip(la, lb)) if x != y), None)
     rel = np.abs(Ea - Eb) / np.abs(Ea)
     digest = hashlib.sha1(repr(la).encode()).hexdigest()[:16]       # compare across PROCESSES by diffing two logs
-    print(json.dumps({"dmrg_twice": f"Heisenberg L={L} chi={chi} f64, 1 sweep, MPS built on {mps_device}",
+    print(json.dumps({"dmrg_twice": f"Heisenberg L={L} chi={chi} f64, 1 sweep, MPS built on {mps_device}, global RNG "
+                                    + ("unseeded" if seed_global is None else f"seeded ({seed_global})"),
                       "records": len(la), "log_digest_run1": digest,
                       "first_records": [list(r) for r in la[:6]], "first_differing_record": None if first is None else [first, la[first][0]],
                       "context": None if first is None else [r[0] for r in la[max(0, first - 3): first + 2]],
@@ -199,6 +202,8 @@ if __name__ == "__main__":
     ap.add_argument("--chi", type=int, default=512)
     ap.add_argument("--L", type=int, default=16)
     ap.add_argument("--big", action="store_true")
+    ap.add_argument("--seed-global", type=int, default=None,
+                    help="torch.manual_seed before each sweep (a zero start vector is re-seeded from the global RNG)")
     ap.add_argument("--sweep-only", action="store_true", help="only the twice-in-one-process DMRG with hashed intermediates")
     args = ap.parse_args()
     if args.big:
@@ -206,7 +211,7 @@ if __name__ == "__main__":
         part2(args.chi, args.L, DEV)
         sys.exit(0)
     if args.sweep_only:
-        part2(args.chi, args.L, DEV)
+        part2(args.chi, args.L, DEV, args.seed_global)
         sys.exit(0)
     part1(args.chi)
     part2(min(args.chi, 256), args.L, "cpu")
