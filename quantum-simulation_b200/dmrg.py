@@ -400,6 +400,19 @@ class DMRG(nn.Module):
         _check_mpo_shapes(self.Ms, self.ML, self.MR, self.chid)
         self.apply_mpo = ApplyMPO(contract_backend)
         self.history = self._empty_history()
+        self.profile = False            # True: device-synchronised wall time per phase of every bond step -> self.timers
+        self.timers = {"theta_build": 0.0, "lanczos": 0.0, "two_site_split": 0.0, "mps_update": 0.0, "env_update": 0.0}
+
+    def _tick(self, phase: Optional[str], t0: float) -> float:
+        """Profiling hook: with ``self.profile`` set, closes ``phase`` (started at ``t0``) and returns the new start."""
+        if not self.profile:
+            return 0.0
+        import time
+        torch.cuda.synchronize()
+        now = time.perf_counter()
+        if phase is not None:
+            self.timers[phase] += now - t0
+        return now
 
     @staticmethod
     def _empty_history() -> dict:
@@ -417,6 +430,7 @@ class DMRG(nn.Module):
         d = self.chid
         sites = range(self.Nsites - 1) if direction == "right" else range(self.Nsites - 2, -1, -1)
         for p in sites:
+            t0 = self._tick(None, 0.0)
             # 1. two-site wavefunction (dmrg.py:633-662)
             if direction == "right":
                 left_t, right_t = B[p], B[p + 1]
@@ -438,6 +452,7 @@ class DMRG(nn.Module):
                                 torch.mul(right_t, sw.to(right_t.dtype).view(1, 1, -1)).reshape(m, t * r))
             chil, chir = l, r
             psi_flat = psi.reshape(-1)
+            t0 = self._tick("theta_build", t0)
 
             # 2. Lanczos ground state of H_eff (dmrg.py:664-675)
             if updateon:
@@ -448,6 +463,8 @@ class DMRG(nn.Module):
                 Ekeep.append(Entemp)
                 self.history["energies"].append(float(Entemp))
 
+            t0 = self._tick("lanczos", t0)
+
             # 3. optional noise, global RNG, uniform [0,1) like the reference (dmrg.py:677-682)
             if noise > 0:
                 noise_vec = torch.rand_like(psi_flat)
@@ -457,6 +474,7 @@ class DMRG(nn.Module):
 
             # 4. SVD + truncation + MPS update (dmrg.py:684-711); large blocks go through the Gram/eigh split (svd.py)
             Uk, S, Vhk, keep = two_site_split(psi_flat.view(chil * d, d * chir), chi, cutoff)
+            t0 = self._tick("two_site_split", t0)
             self.history["discarded_weights"].append(torch.sum(S[keep:] ** 2).real.item())
             self.history["bond_dims"].append(int(keep))
             self.history["sweeps"].append(int(sweep_idx))
@@ -468,11 +486,14 @@ class DMRG(nn.Module):
             sWeight[p + 1] = nn.Parameter(sv.div(denom), requires_grad=False)
             B[p + 1] = nn.Parameter(Vhk.reshape(keep, d, chir), requires_grad=False)
 
+            t0 = self._tick("mps_update", t0)
+
             # 5. environment update (dmrg.py:713-717)
             if direction == "right":
                 env_manager.update_L(p, A[p])
             else:
                 env_manager.update_R(p + 1, B[p + 1])
+            self._tick("env_update", t0)
             if dispon == 2 and updateon:
                 print(f"Sweep: {sweep_idx} of {numsweeps}, Loc: {p}, Energy: {Ekeep[-1]:.6f}")
         return Ekeep

@@ -299,9 +299,9 @@ class CudaEngine:
         self._lib.ops.env_right_rows(Rn, M.contiguous(), B, B_rows, out)
         return out
 
-    def split(self, theta2d, maxdim, cutoff):
+    def split(self, theta2d, maxdim, cutoff, **kw):
         from .svd import two_site_split
-        return two_site_split(theta2d, maxdim, cutoff)
+        return two_site_split(theta2d, maxdim, cutoff, **kw)
 
     def tag(self, env, row0=0):
         """Test an environment (or this rank's row block of one, first row ``row0``) for an identity channel and
@@ -341,8 +341,12 @@ class ShardedDMRG:
         combined and re-sharded with one reduce-scatter; ``update_R`` computes its own row block locally;
       * the right environment of the active bond is all-gathered once per bond step (it multiplies the unsharded
         right bond of theta);
-      * the two-site split runs on rank 0 and its factors are broadcast, so all ranks hold bit-identical MPS
-        tensors (a replicated cuSOLVER call is not guaranteed to be bit-reproducible across devices).
+      * theta is built sharded (every rank forms its rows) and the two-site split of truncating bulk blocks runs ON the
+        row shards (``svd.sketch_split_sharded``: local GEMMs, l x l all-reduces, the small eigh on rank 0 and its
+        result broadcast); other blocks are gathered, split on rank 0 and the factors broadcast -- either way all ranks
+        hold bit-identical MPS tensors (a replicated cuSOLVER call is not guaranteed to be bit-reproducible across
+        devices);
+      * noise (dmrg.py:677-682) is drawn on rank 0 and broadcast.
     """
 
     def __init__(self, mps, mpo, *, device, dtype=torch.float64, group=None, min_shard_chi: int = 64, engine=None,
@@ -367,6 +371,7 @@ class ShardedDMRG:
         self._ops_cache: dict = {}
         self._arena: Optional[SymmetricArena] = None
         self._max_chi = 0
+        self.sharded_split = True       # two-site split on the row shards where the block allows it (svd.py)
         self.profile = False            # True: synchronise around the phases and accumulate seconds in self.timers
         self.timers = {"theta": 0.0, "gather_R": 0.0, "lanczos": 0.0, "split": 0.0, "env": 0.0}
         self.comm = {"all_gather_vec": 0, "all_gather_env": 0, "reduce_scatter_env": 0, "all_reduce_env": 0,
@@ -445,16 +450,16 @@ class ShardedDMRG:
 
     # ---- one bond step ----------------------------------------------------------------------------------
     def _ground_state(self, theta: torch.Tensor, L: _Env, M1, M2, R_full, chi_l: int, kw: dict):
+        """Lanczos on this bond.  Sharded bond: ``theta`` is this rank's row shard (flat) and so is the result;
+        replicated bond: full vectors."""
         per_row = M1.shape[3] * M2.shape[3] * R_full.shape[2]
         if L.sharded:
-            lo, hi = self._block(chi_l)
             op = self._sharded_op(chi_l, per_row, theta.dtype, theta.device)
-            shard = theta.reshape(-1)[lo * per_row: hi * per_row]
-            v, E = lanczos_ground_state_sharded(shard, op, (L.t, M1, M2, R_full), group=self.group,
+            v, E = lanczos_ground_state_sharded(theta.reshape(-1), op, (L.t, M1, M2, R_full), group=self.group,
                                                 _vector_ops=self.engine.vector_ops, **kw)
             self.comm["all_gather_vec"] += 1 + kw["num_restarts"] * kw["krylov_dim"]
             self.comm["sharded_steps"] += 1
-            return gather_rows(v, chi_l, per_row, self.group), E
+            return v, E
         self.comm["replicated_steps"] += 1
         v, E = self.engine.lanczos(theta.reshape(-1), self.engine.apply_mpo, (L.t, M1, M2, R_full), **kw)
         return v, E
@@ -481,14 +486,54 @@ class ShardedDMRG:
             self._ops_cache[key] = op
         return op
 
-    def _split(self, theta2d: torch.Tensor, chi: int, cutoff: float):
+    def _add_noise(self, v: torch.Tensor, noise: float, sharded: bool, chi_l: int) -> torch.Tensor:
+        """The reference's noise term (dmrg.py:677-682: uniform [0,1) vector from the global RNG, normalised, added with
+        weight ``noise``, result renormalised) on a replicated vector or on this rank's row shard.  Rank 0 draws the
+        vector (its global RNG plays the role of the reference's) and broadcasts it, so every rank perturbs the same
+        state whatever the RNG states of the other ranks are."""
+        import torch.distributed as dist
+        n_full = v.numel() * (self.world if sharded else 1)
+        nv = torch.empty(n_full, dtype=v.dtype, device=v.device)
+        if self.rank == 0:
+            nv.copy_(torch.rand_like(nv))
+        dist.broadcast(_real_view(nv), src=dist.get_global_rank(self.group, 0), group=self.group)
+        self.comm["broadcast_noise"] = self.comm.get("broadcast_noise", 0) + 1
+        nv.div_(torch.linalg.norm(nv))
+        if sharded:
+            part = nv.view(self.world, -1)[self.rank]
+            out = v + part * noise
+            n2 = (torch.linalg.norm(out) ** 2).reshape(1)
+            dist.all_reduce(n2, group=self.group)
+            return out.div_(torch.sqrt(n2).to(out.dtype))
+        out = v + nv * noise
+        return out.div_(torch.linalg.norm(out))
+
+    def _split_any(self, v: torch.Tensor, sharded: bool, chil: int, chir: int, chi: int, cutoff: float):
+        """Two-site split of the Lanczos result: on the row shards where the block allows it
+        (``svd.sketch_split_sharded``: nobody gathers theta, only l x l matrices are reduced), else gathered and split on
+        rank 0."""
+        from .svd import sharded_split_eligible, sketch_split_sharded
+        d = self.chid
+        m, n = chil * d, d * chir
+        tried = False
+        if sharded and self.sharded_split and sharded_split_eligible(m, n, chi, self.world):
+            tried = True
+            out = sketch_split_sharded(v.view(m // self.world, n), m, chi, cutoff, self.group, self.comm)
+            if out is not None:
+                self.comm["sharded_splits"] = self.comm.get("sharded_splits", 0) + 1
+                return out
+        theta = gather_rows(v, chil, d * d * chir, self.group) if sharded else v
+        return self._split(theta.reshape(m, n), chi, cutoff, sketch=False if tried else None)
+
+    def _split(self, theta2d: torch.Tensor, chi: int, cutoff: float, sketch=None):
         """Two-site split on rank 0, factors broadcast to everyone."""
         import torch.distributed as dist
         m, n = theta2d.shape
         src = dist.get_global_rank(self.group, 0)
         meta = torch.zeros(2, dtype=torch.int64, device=theta2d.device)
         if self.rank == 0:
-            U, S, Vh, keep = self.engine.split(theta2d, chi, cutoff)
+            kw = {} if sketch is None else {"sketch": sketch}
+            U, S, Vh, keep = self.engine.split(theta2d, chi, cutoff, **kw)
             meta[0], meta[1] = keep, S.numel()
         dist.broadcast(meta, src=src, group=self.group)
         keep, ns = int(meta[0]), int(meta[1])
@@ -516,21 +561,25 @@ class ShardedDMRG:
             torch.cuda.synchronize()
             self._t_last = time.perf_counter()
         for p in sites:
-            if direction == "right":                                  # theta build, replicated (dmrg.py:633-646)
+            # theta build (dmrg.py:633-660).  On a sharded bond every rank builds only ITS rows of theta (the row block
+            # of the left site tensor times the full right one): the sharded Lanczos solver takes exactly that shard
+            if direction == "right":
                 lt, rt, sw = B[p], B[p + 1], sW[p]
-                if sw.dim() == 2:
-                    sw = torch.diagonal(sw, 0)
-                l, s, m = lt.shape
-                _m, t, r = rt.shape
-                psi = self.engine.matmul(torch.mul(lt, sw.to(lt.dtype).view(-1, 1, 1)).reshape(l * s, m), rt.reshape(m, t * r))
-            else:                                                     # (dmrg.py:647-660)
+            else:
                 lt, rt, sw = A[p], A[p + 1], sW[p + 2]
-                if sw.dim() == 2:
-                    sw = torch.diagonal(sw, 0)
-                l, s, m = lt.shape
-                _m, t, r = rt.shape
-                psi = self.engine.matmul(lt.reshape(l * s, m), torch.mul(rt, sw.to(rt.dtype).view(1, 1, -1)).reshape(m, t * r))
+            if sw.dim() == 2:
+                sw = torch.diagonal(sw, 0)
+            l, s, m = lt.shape
+            _m, t, r = rt.shape
             chil, chir = l, r
+            sharded = L[p].sharded
+            lo, hi = self._block(chil) if sharded else (0, l)
+            if direction == "right":
+                left = torch.mul(lt[lo:hi], sw[lo:hi].to(lt.dtype).view(-1, 1, 1)).reshape((hi - lo) * s, m)
+                psi = self.engine.matmul(left, rt.reshape(m, t * r))
+            else:
+                psi = self.engine.matmul(lt[lo:hi].reshape((hi - lo) * s, m),
+                                         torch.mul(rt, sw.to(rt.dtype).view(1, 1, -1)).reshape(m, t * r))
             self._tick("theta")
             R_full = self._tag(self._full(R[p + 2]))
             self._tick("gather_R")
@@ -538,7 +587,9 @@ class ShardedDMRG:
             self._tick("lanczos")
             Ekeep.append(E)
             self.history["energies"].append(float(E))
-            Uk, S, Vhk, keep = self._split(theta.reshape(chil * d, d * chir), params["chi"], params["cutoff"])
+            if params["noise"] > 0:
+                theta = self._add_noise(theta, params["noise"], sharded, chil)
+            Uk, S, Vhk, keep = self._split_any(theta, sharded, chil, chir, params["chi"], params["cutoff"])
             self._tick("split")
             self.history["discarded_weights"].append(torch.sum(S[keep:] ** 2).real.item())
             self.history["bond_dims"].append(int(keep))
@@ -594,9 +645,7 @@ class ShardedDMRG:
         for k in range(1, sweeps.numsweeps + 1):
             params = {"chi": sweeps.maxdim[k - 1], "krydim": sweeps.krylov_dim[k - 1], "cutoff": sweeps.cutoff[k - 1],
                       "reortho": sweeps.reortho[k - 1], "maxreortho": sweeps.maxreortho[k - 1], "dispon": dispon,
-                      "maxit": maxit, "sweep_idx": k, "numsweeps": sweeps.numsweeps}
-            if sweeps.noise[k - 1] > 0:
-                raise ValueError("ShardedDMRG does not support noise > 0 (the reference's noise uses the global RNG)")
+                      "maxit": maxit, "sweep_idx": k, "numsweeps": sweeps.numsweeps, "noise": sweeps.noise[k - 1]}
             self._sweep("right", L, R, params, Ekeep)
             self.mps.ortho_center = N - 1
             sw = self.mps.sWeight[N - 1]                                            # dmrg.py:769-781

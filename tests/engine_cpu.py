@@ -35,9 +35,9 @@ class CpuEngine:
         return torch.einsum("wvps,vxb,ksb,apx->wak", M, Rn, B, B_rows.conj()).contiguous()
 
     @staticmethod
-    def split(theta2d, maxdim, cutoff):
+    def split(theta2d, maxdim, cutoff, **kw):
         from quantum_simulation_b200.svd import two_site_split
-        return two_site_split(theta2d, maxdim, cutoff)
+        return two_site_split(theta2d, maxdim, cutoff, **kw)
 
     @staticmethod
     def lanczos(v, op, args, **kw):

@@ -160,6 +160,9 @@ def case_c3full():
     sw = qsb.Sweeps(1)
     sw.set_schedule(maxdim=[2048], cutoff=[0.0], krylov_dim=[4], noise=[0.0])
     dm = quiet(qsb.DMRG, mps, [m.to(DEV) for m in mpo("heis_f64_L100", dt)], device=DEV, dtype=dt)
+    import quantum_simulation_b200.svd as _qsvd
+    _qsvd.TIMING = "--split-timing" in sys.argv
+    dm.profile = "--split-timing" in sys.argv
     torch.manual_seed(1)       # zero centre tensor at this size -> first Lanczos start is a global-RNG draw
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -170,11 +173,81 @@ def case_c3full():
     return [{"case": "C3 Heisenberg L=100 chi=2048 f64: one full sweep (198 bond updates), measured",
              "mps_init_on_gpu_s": t_init, "sweep_s": t_sweep, "E_end_of_sweep": float(E[-1]),
              "E_mid_right": float(E[98]), "bond_dim_max": int(max(bd)), "updates_at_full_chi": int(sum(b == 2048 for b in bd)),
-             "peak_memory_GB": torch.cuda.max_memory_allocated() / 1e9}]
+             "peak_memory_GB": torch.cuda.max_memory_allocated() / 1e9,
+             "phase_seconds": dict(dm.timers) if dm.profile else None,
+             "split_paths": dict(__import__("quantum_simulation_b200").svd.stats),
+             "discarded_weight_max": float(max(dm.history["discarded_weights"])),
+             "discarded_weight_max_full_chi": float(max(w for w, b in zip(dm.history["discarded_weights"], bd) if b == 2048))}]
+
+
+def case_split():
+    """Stage timing of the two-site split at the C3 bulk shape (4096 x 4096 float64, keep 2048) on a block with a
+    DMRG-like spectrum: the range-compressed path against the full Gram/eigh path."""
+    from quantum_simulation_b200 import svd as qsvd
+    dt = torch.float64
+    n, k = 4096, 2048
+    g = torch.Generator(device=DEV).manual_seed(11)
+    a = torch.randn(n, n, dtype=dt, device=DEV, generator=g)
+    U0 = torch.linalg.qr(a)[0]
+    V0 = torch.linalg.qr(a.T.contiguous())[0]
+    rows = []
+    for decay in (60.0, 30.0):
+        sv = torch.exp(-torch.arange(n, dtype=dt, device=DEV) * (decay / n) * 8)
+        theta = (U0 * sv) @ V0.T
+        theta = theta / torch.linalg.norm(theta)
+
+        def tm(fn, reps=3):
+            fn(); torch.cuda.synchronize()
+            best = 1e9
+            for _ in range(reps):
+                t0 = time.perf_counter(); r = fn(); torch.cuda.synchronize()
+                best = min(best, time.perf_counter() - t0)
+            return best * 1e3, r
+        t_gram, (Ug, Sg, Vg, kg) = tm(lambda: qsvd._gram_split(theta, k, 0.0))
+        qsvd._backoff.clear()
+        t_sk, out = tm(lambda: qsvd._sketch_split(theta, k, 0.0))
+        l = k + qsvd._oversample(k)
+        om = qsvd._omega(n, l, dt, theta.device)
+        t_y, Y = tm(lambda: qsvd._mm(theta, om))
+        regs = {}
+        for reg in (1e-9, 1e-10, 1e-11, 1e-12):
+            Yr = Y + qsvd._fixed_normal("reg", n, l, dt, theta.device, 0xB200) * (reg * float(torch.linalg.norm(Y)) / (n * l) ** 0.5)
+            for sp in (1, 2, 3):
+                t_, Qr = tm(lambda: qsvd._orthonormal_cols(Yr, sp), 1)
+                if Qr is not None:
+                    regs[f"reg{reg:g}_passes{sp}"] = {"ms": t_, "rho": float(torch.linalg.norm(theta - Qr @ (Qr.T @ theta)) ** 2),
+                                                      "orth": float((Qr.T @ Qr - torch.eye(l, dtype=dt, device=DEV)).abs().max())}
+                else:
+                    regs[f"reg{reg:g}_passes{sp}"] = {"ms": t_, "failed": True}
+        t_q, Q = tm(lambda: qsvd._orthonormal_cols(Y))
+        t_hq, _ = tm(lambda: torch.linalg.qr(Y)[0])
+        if Q is None:
+            Q = torch.linalg.qr(Y)[0]
+        t_b, B = tm(lambda: qsvd._mm(Q.T, theta))
+        t_r, _ = tm(lambda: torch.linalg.norm(theta - qsvd._mm(Q, B)))
+        Gs = qsvd._mm(B, B.T)
+        t_e, _ = tm(lambda: torch.linalg.eigh(Gs))
+        t_e4, _ = tm(lambda: torch.linalg.eigh(qsvd._mm(theta, theta.T)))
+        Bk = B[:k].contiguous()
+        t_o, _ = tm(lambda: qsvd._orthonormal_rows(Bk))
+        row = {"case": f"two-site split 4096x4096 f64 keep 2048, S_j ~ exp(-{decay * 8 / n:.3f} j)", "gram_split_ms": t_gram,
+               "sketch_split_ms": t_sk, "sketch_accepted": out is not None, "rho": qsvd.stats["last_rho"],
+               "stages_ms": {"Y=theta*Omega": t_y, "sCholQR3(Y)": t_q, "cholqr_ok": qsvd._orthonormal_cols(Y) is not None,
+                             "householder_qr(Y)": t_hq, "B=Q^H theta": t_b, "residual": t_r, f"eigh({l})": t_e,
+                             "eigh(4096)+gram": t_e4, "orthonormal_rows(k x n)": t_o},
+               "regularised_cholqr": regs}
+        if out is not None:
+            U, S, Vh, keep = out
+            row["S2_maxdev"] = float((S[:k] ** 2 - Sg[:k] ** 2).abs().max())
+            row["rec_dev"] = float(torch.linalg.norm((U * S[:k]) @ Vh - (Ug * Sg[:k]) @ Vg))
+            row["iso_dev"] = [float(torch.linalg.norm(U.T @ U - torch.eye(k, dtype=dt, device=DEV))),
+                              float(torch.linalg.norm(Vh @ Vh.T - torch.eye(k, dtype=dt, device=DEV)))]
+        rows.append(row)
+    return rows
 
 
 if __name__ == "__main__":
     which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["c1"]
     for w in which:
-        for row in {"c1": case_c1, "c2": case_c2, "c3": case_c3, "svd": case_svd, "c3full": case_c3full}[w]():
+        for row in {"c1": case_c1, "c2": case_c2, "c3": case_c3, "svd": case_svd, "c3full": case_c3full, "split": case_split}[w]():
             print(json.dumps(row), flush=True)

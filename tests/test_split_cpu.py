@@ -28,7 +28,9 @@ def _reference_keep(S, maxdim, cutoff):
 @pytest.mark.parametrize("dtype", [torch.float64, torch.complex128])
 @pytest.mark.parametrize("shape", [(96, 96), (64, 160), (160, 64), (1, 8), (8, 1), (2, 2)])
 @pytest.mark.parametrize("maxdim,cutoff", [(10 ** 6, 0.0), (24, 0.0), (10 ** 6, 1e-10), (5, 1e-6)])
-def test_gram_split_matches_svd(dtype, shape, maxdim, cutoff):
+def test_gram_split_matches_svd(dtype, shape, maxdim, cutoff, monkeypatch):
+    from quantum_simulation_b200 import svd as qsvd
+    monkeypatch.setattr(qsvd, "SKETCH", False)                 # the full Gram/eigh path (the sketch has its own tests)
     m, n = shape
     theta, _ = _matrix(m, n, dtype, 0.2, seed=m * 1000 + n)
     U, S, Vh, keep = two_site_split(theta, maxdim, cutoff, fast_min=1)          # force the Gram/eigh path
@@ -51,7 +53,22 @@ def test_gram_split_matches_svd(dtype, shape, maxdim, cutoff):
     assert keep2 == keep and torch.allclose(S2, Se)
 
 
-def test_gram_split_rank_deficient_and_degenerate():
+def test_gram_split_rank_deficient_and_degenerate(monkeypatch):
+    from quantum_simulation_b200 import svd as qsvd
+    monkeypatch.setattr(qsvd, "SKETCH", False)
+    _rank_deficient_and_degenerate(1e-12)
+
+
+def test_sketched_split_rank_deficient_and_degenerate(monkeypatch):
+    """Same blocks through the range compression: reconstruction to the regularisation amplitude (1e-10 relative)."""
+    from quantum_simulation_b200 import svd as qsvd
+    monkeypatch.setattr(qsvd, "_backoff", {})
+    before = qsvd.stats["sketch_accepted"]
+    _rank_deficient_and_degenerate(1e-9)
+    assert qsvd.stats["sketch_accepted"] >= before + 2
+
+
+def _rank_deficient_and_degenerate(rec_tol):
     """Exactly degenerate and exactly zero singular values (product states, symmetry multiplets): still isometric
     factors and the right weights; the arbitrary rotation inside a degenerate multiplet does not matter."""
     g = torch.Generator().manual_seed(3)
@@ -64,10 +81,75 @@ def test_gram_split_rank_deficient_and_degenerate():
     assert torch.allclose(S[:7], s[:7], atol=1e-12) and float(S[7:].max()) < 1e-7
     assert float(torch.linalg.norm(U.T @ U - torch.eye(7, dtype=torch.float64))) < 1e-12
     assert float(torch.linalg.norm(Vh @ Vh.T - torch.eye(7, dtype=torch.float64))) < 1e-12
-    assert float(torch.linalg.norm((U * S[:7]) @ Vh - theta)) < 1e-12
+    assert float(torch.linalg.norm((U * S[:7]) @ Vh - theta)) < rec_tol
     U, S, Vh, keep = two_site_split(theta, 100, 1e-12, fast_min=1)              # cutoff drops the numerical zeros
     assert keep == 7
     rank1 = torch.outer(Q1[:, 0], Q2[:, 0])
     U, S, Vh, keep = two_site_split(rank1, 4, 0.0, fast_min=1)
     assert keep == 4 and abs(float(S[0]) - 1.0) < 1e-12
     assert float(torch.linalg.norm(U.T @ U - torch.eye(4, dtype=torch.float64))) < 1e-12
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.complex128])
+@pytest.mark.parametrize("shape,k,decay", [((256, 256), 64, 0.3), ((256, 320), 64, 0.25), ((320, 256), 64, 0.25),
+                                           ((192, 192), 40, 0.5)])
+def test_sketched_split_accepted_when_the_tail_is_negligible(dtype, shape, k, decay, monkeypatch):
+    """Range compression in front of the Gram/eigh path (svd._sketch_split): taken for truncating blocks, accepted only
+    when theta has <= 1e-13 of its weight outside the compressed range, and then as accurate as the full path: squared
+    Schmidt values within rho, isometric factors, the optimally truncated block reproduced to sqrt(rho)."""
+    from quantum_simulation_b200 import svd as qsvd
+    monkeypatch.setattr(qsvd, "_backoff", {})
+    m, n = shape
+    theta, _ = _matrix(m, n, dtype, decay, seed=m + n + k)
+    theta = theta / torch.linalg.norm(theta)
+    before = dict(qsvd.stats)
+    U, S, Vh, keep = two_site_split(theta, k, 0.0, fast_min=1)
+    assert qsvd.stats["sketch_accepted"] == before["sketch_accepted"] + 1 and qsvd.stats["last_rho"] <= 1e-13
+    Ue, Se, Vhe = torch.linalg.svd(theta, full_matrices=False)
+    assert keep == k and U.shape == (m, k) and Vh.shape == (k, n)
+    l = k + qsvd._oversample(k)
+    assert S.numel() == l + 1                                  # leading l values + the residual pseudo-value
+    assert float((S[:l] ** 2 - Se[:l] ** 2).abs().max()) <= 2e-13
+    assert abs(float((S[keep:] ** 2).sum()) - float((Se[keep:] ** 2).sum())) <= 2e-13      # discarded weight
+    eye = torch.eye(k, dtype=dtype)
+    assert float(torch.linalg.norm(U.conj().T @ U - eye)) < 1e-12
+    assert float(torch.linalg.norm(Vh @ Vh.conj().T - eye)) < 1e-12
+    rec = (U * S[:keep].to(dtype)) @ Vh
+    best = (Ue[:, :keep] * Se[:keep].to(dtype)) @ Vhe[:keep]
+    assert float(torch.linalg.norm(rec - best)) < 1e-6
+    # a cutoff that bites inside the kept range gives the reference's keep
+    U2, S2, Vh2, keep2 = two_site_split(theta, k, 1e-9, fast_min=1)
+    assert keep2 == _reference_keep(Se, k, 1e-9)
+
+
+def test_sketched_split_rejected_when_the_tail_matters(monkeypatch):
+    """Slowly decaying spectrum: the compressed range misses weight >> 1e-13, the sketch is rejected, the full Gram path
+    answers (identical to calling it directly), and the next blocks of that shape skip the attempt."""
+    from quantum_simulation_b200 import svd as qsvd
+    monkeypatch.setattr(qsvd, "_backoff", {})
+    theta, _ = _matrix(256, 256, torch.float64, 0.02, seed=9)
+    before = dict(qsvd.stats)
+    U, S, Vh, keep = two_site_split(theta, 64, 0.0, fast_min=1)
+    assert qsvd.stats["sketch_rejected"] == before["sketch_rejected"] + 1 and qsvd.stats["last_rho"] > 1e-13
+    Ug, Sg, Vhg, kg = qsvd._gram_split(theta, 64, 0.0)
+    assert keep == kg and torch.equal(S, Sg) and torch.equal(U, Ug) and torch.equal(Vh, Vhg)
+    two_site_split(theta, 64, 0.0, fast_min=1)
+    assert qsvd.stats["sketch_skipped"] == before["sketch_skipped"] + 1
+    assert qsvd.stats["sketch_rejected"] == before["sketch_rejected"] + 1
+
+
+def test_sketched_split_rank_deficient_block():
+    """Exact low rank (first sweeps from a product-like state): the shifted CholeskyQR3 breaks down or flags itself,
+    Householder QR takes over, the result is still the exact split."""
+    from quantum_simulation_b200 import svd as qsvd
+    g = torch.Generator().manual_seed(5)
+    A = torch.randn(256, 12, dtype=torch.float64, generator=g)
+    Bm = torch.randn(12, 256, dtype=torch.float64, generator=g)
+    theta = A @ Bm
+    theta = theta / torch.linalg.norm(theta)
+    U, S, Vh, keep = two_site_split(theta, 64, 0.0, fast_min=1)
+    Se = torch.linalg.svdvals(theta)
+    assert keep == 64 and float((S[:12] - Se[:12]).abs().max()) < 1e-13
+    assert float(torch.linalg.norm((U * S[:keep]) @ Vh - theta)) < 1e-7
+    eye = torch.eye(64, dtype=torch.float64)
+    assert float(torch.linalg.norm(U.T @ U - eye)) < 1e-12 and float(torch.linalg.norm(Vh @ Vh.T - eye)) < 1e-12
