@@ -65,6 +65,8 @@ def parse():
                     help="N>1: how theta shards are exchanged (auto = fused P2P push if available, else NCCL)")
     ap.add_argument("--dense-env", action="store_true",
                     help="fully random L and R (no identity channels): the round-1 workload, nothing is skipped")
+    ap.add_argument("--serial-e2e", action="store_true",
+                    help="N > 1: time the e2e leg as copy -> fused matvec -> copy (the r01 path) instead of forward_host")
     ap.add_argument("--no-sweep", action="store_true", help="skip the measured full DMRG sweep of the extras leg")
     ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / lanczos / env / library legs")
     return ap.parse_args()
@@ -449,6 +451,8 @@ def run_ours(args):
         h_in.copy_(theta_shard.cpu())
         d_in = torch.empty_like(theta_shard)
 
+    e2e_mode = "serial"
+
     def step_e2e():
         d_in.copy_(h_in, non_blocking=True)
         if fused is not None:
@@ -464,6 +468,12 @@ def run_ours(args):
     if world == 1:      # the public call itself takes the pinned host vector: upload, matvec, download pipelined
         def step_e2e():                                    # noqa: F811
             op(h_in, L, M1, M2, R, out=h_out)
+    elif fused is not None and not args.serial_e2e:
+        # N > 1: the fused operator's host-resident call -- shard uploaded in column blocks straight into the gathered
+        # buffer, blocks forwarded to the peers as they land, grid-gated step-1 GEMM, row-block download overlapped
+        def step_e2e():                                    # noqa: F811
+            fused.forward_host(h_in, L, M1, M2, R, h_out)
+        e2e_mode = "pipelined"
 
     for _ in range(2):
         step_e2e()
@@ -479,10 +489,13 @@ def run_ours(args):
            "d2h_bytes_per_step": n * es, "ms_per_step": sec_e / Ke * 1e3, "steps": Ke,
            "bytes_note": "whole-job bytes per step, summed over ranks (each rank moves 1/N of them)",
            "host_pipeline_mode": (next(iter(qsb.ApplyMPO._host_pipes.values()), {}).get("last_mode")
-                                  if world == 1 else None),
+                                  if world == 1 else e2e_mode),
            "call": ("quantum_simulation_b200.ApplyMPO.forward(pinned host psi, out=pinned host) -- chunked upload gating "
                     "the step-1 GEMM, row-block download overlapped" if world == 1 else
-                    "quantum_simulation_b200.parallel.FusedShardedApplyMPO / ShardedApplyMPO")
+                    "quantum_simulation_b200.parallel.FusedShardedApplyMPO.forward_host(pinned host shard, pinned host "
+                    "rows) -- column-block upload into the gathered buffer, block-wise P2P forwarding, grid-gated step-1 "
+                    "GEMM, row-block download overlapped" if e2e_mode == "pipelined" else
+                    "quantum_simulation_b200.parallel.FusedShardedApplyMPO / ShardedApplyMPO, copies around it")
                    + " (torch.ops.qsb200.heff_apply* -> qsb_heff_apply)"}
 
     exec_tf = flops_exec_local * world / (sec / K) / 1e12

@@ -86,7 +86,12 @@ typedef struct {
     int chunk_axis;         /* 0: the blocks are ROW blocks of theta (the k range of step 1; multi-GPU exchange).
                                1: the blocks are COLUMN blocks of theta viewed as (chi_l_in, d1*d2*chi_r): an output tile
                                   of step 1 then depends on ONE block only, so tiles start as soon as their block has
-                                  landed (host upload with qsb_upload_columns); chunk_rot / chunk_local are ignored. */
+                                  landed (host upload with qsb_upload_columns); chunk_rot / chunk_local are ignored.
+                               2: a GRID of n_chunks row blocks x chunk_cols column blocks, flag index
+                                  row_block * chunk_cols + column_block: every rank uploads its row shard of a HOST-resident
+                                  theta in column blocks and forwards each block to its peers (qsb_upload_columns +
+                                  qsb_push_columns_dma), and tiles of column block j start once (r, j) is there for the
+                                  row block r they are reading. */
     int chunk_local;        /* 1: block chunk_rot is already in place (stream-ordered before this call), do not gate it.
                                Required when that block is copied on the SAME device: such a copy may need SMs, which the
                                persistent GEMM would be holding while it waits for the flag. */
@@ -100,6 +105,7 @@ typedef struct {
     int L_identity;         /* 1 + w with L[w][a'][a] == delta(a, a' + L_row0) */
     int R_identity;         /* 1 + w with R[w][b'][b] == delta(b, b') */
     int L_row0;             /* first row of the bra index held by a row-sharded L (multi-GPU), else 0 */
+    int chunk_cols;         /* chunk_axis == 2: number of column blocks per row block (else ignored) */
 } qsb_heff_desc;
 
 int qsb_heff_workspace_bytes(const qsb_heff_desc* d, size_t* bytes);
@@ -136,6 +142,13 @@ int qsb_push_shard_dma(const void* src, size_t bytes, void* const* dst, int* con
    (cudaMemcpy2DAsync), each followed by a stream-ordered flag write flags[c] = epoch; pairs with chunk_axis = 1. */
 int qsb_upload_columns(const void* src_host, void* dst, int64_t rows, int64_t row_elems, int elem_bytes, int n_chunks,
                        int* flags, int epoch, void* stream);
+
+/* Forward a (rows x row_elems) row-major device block to `count` peers in n_chunks column blocks on the copy engines: for
+   each column block c, first a stream-ordered wait until ready_flags[c] >= epoch (cuStreamWaitValue32: the block has been
+   uploaded into `src` by qsb_upload_columns on another stream), then per destination one cudaMemcpy2DAsync into dst[i]
+   (same pitch) and a flag write flag[i][c] = epoch.  Pairs with chunk_axis = 2. */
+int qsb_push_columns_dma(const void* src, int64_t rows, int64_t row_elems, int elem_bytes, int n_chunks,
+                         const int* ready_flags, void* const* dst, int* const* flag, int count, int epoch, void* stream);
 
 /* ---- environment updates (dmrg.py:254-308) ----------------------------- */
 typedef struct {

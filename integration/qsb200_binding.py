@@ -38,7 +38,8 @@ class HeffDesc(C.Structure):                      # == qsb_heff_desc (include/qs
                 ("n_chunks", C.c_int), ("chunk_rot", C.c_int), ("chunk_epoch", C.c_int),
                 ("chunk_flags", C.c_void_p),
                 ("chunk_axis", C.c_int), ("chunk_local", C.c_int),
-                ("L_identity", C.c_int), ("R_identity", C.c_int), ("L_row0", C.c_int)]
+                ("L_identity", C.c_int), ("R_identity", C.c_int), ("L_row0", C.c_int),
+                ("chunk_cols", C.c_int)]
 
 
 class EnvDesc(C.Structure):                       # == qsb_env_desc

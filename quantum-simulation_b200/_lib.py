@@ -32,6 +32,7 @@ EXPORTS = [
     "qsb_env_workspace_bytes", "qsb_env_left", "qsb_env_right", "qsb_env_flops",
     "qsb_lz_scratch_bytes", "qsb_lz_dot", "qsb_lz_axpy_norm", "qsb_lz_scale", "qsb_lz_combine",
     "qsb_strided_copy3", "qsb_gemm", "qsb_probe_dmma", "qsb_push_shard", "qsb_push_shard_dma", "qsb_upload_columns",
+    "qsb_push_columns_dma",
     "qsb_heff_flops_executed", "qsb_env_identity_deviation",
     "qsb_sizeof_heff_desc", "qsb_sizeof_env_desc", "qsb_sizeof_gemm_desc",
 ]
@@ -53,7 +54,7 @@ class HeffDesc(C.Structure):
         ("chunk_flags", C.c_void_p),
         ("chunk_axis", C.c_int),
         ("chunk_local", C.c_int),
-        ("L_identity", C.c_int), ("R_identity", C.c_int), ("L_row0", C.c_int),
+        ("L_identity", C.c_int), ("R_identity", C.c_int), ("L_row0", C.c_int), ("chunk_cols", C.c_int),
     ]
 
 
@@ -127,6 +128,7 @@ def load() -> C.CDLL:
     lib.qsb_push_shard.argtypes = [vp, C.c_size_t, C.POINTER(vp), C.POINTER(vp), i32, i32, vp, vp]
     lib.qsb_upload_columns.argtypes = [vp, vp, i64, i64, i32, i32, vp, i32, vp]
     lib.qsb_push_shard_dma.argtypes = [vp, C.c_size_t, C.POINTER(vp), C.POINTER(vp), i32, i32, vp]
+    lib.qsb_push_columns_dma.argtypes = [vp, i64, i64, i32, i32, vp, C.POINTER(vp), C.POINTER(vp), i32, i32, vp]
     lib.qsb_probe_dmma.argtypes = [i32, C.POINTER(C.c_double), vp, vp]
     lib.qsb_heff_flops_executed.argtypes = [C.POINTER(HeffDesc)]
     lib.qsb_heff_flops_executed.restype = C.c_double
@@ -332,6 +334,7 @@ def _impl_heff_apply(psi, L, M1, M2, R, out, gate=None, ident=(-1, -1, 0)) -> No
     if gate is not None:                   # (flags tensor, n_chunks, rot, epoch): fused all-gather -> matvec
         flags, d.n_chunks, d.chunk_rot, d.chunk_epoch, d.chunk_local = gate[:5]
         d.chunk_axis = gate[5] if len(gate) > 5 else 0
+        d.chunk_cols = gate[6] if len(gate) > 6 else 0
         d.chunk_flags = flags.data_ptr()
     nb = C.c_size_t(0)
     check(lib.qsb_heff_workspace_bytes(C.byref(d), C.byref(nb)), "ApplyMPO")
@@ -356,6 +359,26 @@ def _impl_heff_apply_colgated(psi, L, M1, M2, R, out, flags, n_chunks: int, epoc
                               l_ident: int = -1, r_ident: int = -1, l_row0: int = 0) -> None:
     _impl_heff_apply(psi, L, M1, M2, R, out, gate=(flags, n_chunks, 0, epoch, 0, 1),
                      ident=(l_ident, r_ident, l_row0))
+
+
+def _impl_heff_apply_gridgated(psi, L, M1, M2, R, out, flags, n_rows: int, n_cols: int, rot: int, epoch: int,
+                               l_ident: int = -1, r_ident: int = -1, l_row0: int = 0) -> None:
+    """theta arrives in n_rows row blocks (source ranks) x n_cols column blocks, flags[r * n_cols + c] >= epoch."""
+    _impl_heff_apply(psi, L, M1, M2, R, out, gate=(flags, n_rows, rot, epoch, 0, 2, n_cols),
+                     ident=(l_ident, r_ident, l_row0))
+
+
+def push_columns_dma(src: torch.Tensor, rows: int, row_elems: int, n_chunks: int, ready_flags: torch.Tensor,
+                     dst_ptrs: Sequence[int], flag_ptrs: Sequence[int], epoch: int) -> None:
+    """Forward a device block to peers column block by column block as the blocks land (see qsb_push_columns_dma), on the
+    CURRENT stream (callers use side streams)."""
+    dev = _require_cuda(src, ready_flags)
+    cnt = len(dst_ptrs)
+    dp = (C.c_void_p * max(cnt, 1))(*[C.c_void_p(int(p)) for p in dst_ptrs])
+    fp = (C.c_void_p * max(cnt, 1))(*[C.c_void_p(int(p)) for p in flag_ptrs])
+    with torch.cuda.device(dev):
+        check(load().qsb_push_columns_dma(src.data_ptr(), rows, row_elems, src.element_size(), n_chunks,
+                                          ready_flags.data_ptr(), dp, fp, cnt, epoch, _stream()), "push_columns_dma")
 
 
 def upload_columns(src_host: torch.Tensor, dst: torch.Tensor, rows: int, row_elems: int, n_chunks: int,
@@ -589,6 +612,8 @@ def register_ops() -> None:
               "int n_chunks, int rot, int epoch, int local, int l_ident=-1, int r_ident=-1, int l_row0=0) -> ()")
     tl.define("heff_apply_colgated(Tensor psi, Tensor L, Tensor M1, Tensor M2, Tensor R, Tensor(a!) out, Tensor flags, "
               "int n_chunks, int epoch, int l_ident=-1, int r_ident=-1, int l_row0=0) -> ()")
+    tl.define("heff_apply_gridgated(Tensor psi, Tensor L, Tensor M1, Tensor M2, Tensor R, Tensor(a!) out, Tensor flags, "
+              "int n_rows, int n_cols, int rot, int epoch, int l_ident=-1, int r_ident=-1, int l_row0=0) -> ()")
     tl.define("push_shard(Tensor src, int[] dst_ptrs, int[] flag_ptrs, int epoch, Tensor(a!) ticket) -> ()")
     tl.define("env_left(Tensor env, Tensor M, Tensor site, Tensor(a!) out, int ident=-1) -> ()")
     tl.define("env_right(Tensor env, Tensor M, Tensor site, Tensor(a!) out, int ident=-1) -> ()")
@@ -605,6 +630,7 @@ def register_ops() -> None:
     tl.impl("heff_apply_ident", _impl_heff_apply_ident, "CUDA")
     tl.impl("heff_apply_gated", _impl_heff_apply_gated, "CUDA")
     tl.impl("heff_apply_colgated", _impl_heff_apply_colgated, "CUDA")
+    tl.impl("heff_apply_gridgated", _impl_heff_apply_gridgated, "CUDA")
     tl.impl("push_shard", _impl_push_shard, "CUDA")
     tl.impl("env_left", _impl_env_left, "CUDA")
     tl.impl("env_right", _impl_env_right, "CUDA")

@@ -417,6 +417,10 @@ extern "C" int qsb_heff_apply(const qsb_heff_desc* d, void* stream_) {
             g1.kepoch = d->chunk_epoch; g1.kflags = d->chunk_flags;
             if (d->chunk_axis == 1) { g1.nsplit = d->n_chunks; }
             else { g1.ksplit = d->n_chunks; g1.krot = d->chunk_rot; g1.klocal = d->chunk_local; }
+            if (d->chunk_axis == 2) {            // row blocks (source ranks) x column blocks (upload order)
+                if (d->chunk_cols < 1) return QSB_ERR_ARG;
+                g1.nsplit = d->chunk_cols;
+            }
             g1.force_path = 1;
         }
         if ((rc = gemm_launch(g1, stream))) return rc;
@@ -609,6 +613,48 @@ extern "C" int qsb_push_shard_dma(const void* src, size_t bytes, void* const* ds
         int rc = check_cuda(cudaMemcpyAsync(dst[i], src, bytes, cudaMemcpyDefault, stream));   // peer, local or pinned host source
         if (rc) return rc;
         if (wv((CUstream)stream, (CUdeviceptr)flag[i], (cuuint32_t)epoch, 0) != CUDA_SUCCESS) return QSB_ERR_LAUNCH;
+    }
+    return QSB_OK;
+}
+
+typedef CUresult (*WaitValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+static WaitValue32Fn get_wait_value32() {
+    static WaitValue32Fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (WaitValue32Fn)p;
+        (void)cudaGetLastError();
+    }
+    return fn;
+}
+
+extern "C" int qsb_push_columns_dma(const void* src, int64_t rows, int64_t row_elems, int elem_bytes, int n_chunks,
+                                    const int* ready_flags, void* const* dst, int* const* flag, int count, int epoch,
+                                    void* stream_) {
+    if (!src || !ready_flags || !dst || !flag || rows < 1 || row_elems < 1 || n_chunks < 1 || elem_bytes < 1 ||
+        count < 0 || count > qsb::kMaxPeers)
+        return QSB_ERR_ARG;
+    if (row_elems % n_chunks != 0) return QSB_ERR_SHAPE;
+    WriteValue32Fn wv = get_write_value32();
+    WaitValue32Fn ww = get_wait_value32();
+    if (!wv || !ww) return QSB_ERR_DEVICE;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const size_t pitch = (size_t)row_elems * elem_bytes, width = pitch / n_chunks;
+    for (int c = 0; c < n_chunks; ++c) {
+        // the column block is in `src` once the uploading stream has published it (CU_STREAM_WAIT_VALUE_GEQ)
+        if (ww((CUstream)stream, (CUdeviceptr)(ready_flags + c), (cuuint32_t)epoch, 0x0) != CUDA_SUCCESS) return QSB_ERR_LAUNCH;
+        for (int i = 0; i < count; ++i) {
+            if (!dst[i] || !flag[i]) return QSB_ERR_ARG;
+            int rc = check_cuda(cudaMemcpy2DAsync((char*)dst[i] + c * width, pitch, (const char*)src + c * width, pitch,
+                                                  width, (size_t)rows, cudaMemcpyDefault, stream));
+            if (rc) return rc;
+            if (wv((CUstream)stream, (CUdeviceptr)(flag[i] + c), (cuuint32_t)epoch, 0) != CUDA_SUCCESS) return QSB_ERR_LAUNCH;
+        }
     }
     return QSB_OK;
 }

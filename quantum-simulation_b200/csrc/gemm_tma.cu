@@ -47,7 +47,8 @@ struct TArgs {
     // kflags[c] >= kepoch (set by the peer that pushed it); chunks are visited starting from chunk krot
     int raster;                 // tile rows per rasterisation group
     int ksplit, krot, kepoch, klocal;    // klocal: chunk krot is already in place, never wait for it
-    int nsplit;                          // > 1: whole tiles are gated on the column block of B they read (kflags)
+    int nsplit;                          // > 1: whole tiles are gated on the column block of B they read (kflags);
+                                         // with ksplit > 1 too: flag kflags[kc * nsplit + column block] per k chunk
     int Zb;                              // batch count (needed for the n-outermost tile order of nsplit mode)
     const int* kflags;
 };
@@ -253,7 +254,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             int tm, tn;
             tile_map<GATED>(g.nsplit, g.tiles_m, g.tiles_n, g.Zb, g.raster, p_tile, tm, tn, p_z);
             p_m0 = tm * C::BM; p_n0 = tn * C::BN;
-            if (GATED && g.nsplit > 1) {     // column-block gating: this tile reads one block of B, wait for it once
+            if (GATED && g.nsplit > 1 && g.ksplit <= 1) {     // column-block gating: this tile reads one block of B, wait for it once
                 const int c = (int)((long long)p_n0 * g.nsplit / g.N);
                 if (c != p_chunk_ok) {
                     int v;
@@ -274,15 +275,17 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             const int per = ktiles / g.ksplit;
             const int c = p_it / per;
             int kc = c + g.krot; if (kc >= g.ksplit) kc -= g.ksplit;
-            if (kc != p_chunk_ok && !(g.klocal && kc == g.krot)) {     // the local block is never gated
+            // grid gating (nsplit > 1 as well): theta arrives in ksplit row blocks x nsplit column blocks, one flag each
+            const int fi = g.nsplit > 1 ? kc * g.nsplit + (int)((long long)p_n0 * g.nsplit / g.N) : kc;
+            if (fi != p_chunk_ok && !(g.klocal && kc == g.krot)) {     // the local block is never gated
                 int v;
                 const long long t0 = clock64();
                 do {
-                    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(g.kflags + kc) : "memory");
+                    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(g.kflags + fi) : "memory");
                     if (v < g.kepoch && clock64() - t0 > 100000000000LL) __trap();     // ~50 s: peer never pushed
                 } while (v < g.kepoch);
                 asm volatile("fence.proxy.async.global;" ::: "memory");   // peer-written data -> TMA (async proxy) reads
-                p_chunk_ok = kc;
+                p_chunk_ok = fi;
             }
             p = 0;
             k0 = (kc * per + (p_it - c * per)) * C::BK;

@@ -130,6 +130,11 @@ class SymmetricArena:
         self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
         self.flags = self.store[:256].view(torch.int32)
         self.flag_ptrs = [self.ptrs[r] + 4 * self.rank for r in range(self.world)]
+        # second half of the flag block: the (source rank x column block) grid of the host-resident path
+        self.grid_cols = max(1, min(8, 32 // self.world))
+        self.grid_flags = self.flags[32:]
+        self.grid_flag_ptrs = [self.ptrs[r] + 4 * (32 + self.rank * self.grid_cols) for r in range(self.world)]
+        self.copy_streams = {"h2d": torch.cuda.Stream(device=device), "d2h": torch.cuda.Stream(device=device)}
         self.ticket = torch.zeros(1, dtype=torch.int32, device=device)
         self.side = [torch.cuda.Stream(device=device) for _ in range(2)]
         self.epoch = 0
@@ -242,6 +247,84 @@ class FusedShardedApplyMPO:
         for done in dones:
             main.wait_event(done)        # v_shard may be reused once our outgoing copies have left
         return out
+
+    # ---- host-resident call: theta shard in pinned host memory, result rows to pinned host memory ---------------
+    def forward_host(self, v_host: torch.Tensor, L_rows, M1, M2, R, out_host: torch.Tensor) -> torch.Tensor:
+        """The same sharded matvec with this rank's shard of theta in PINNED HOST memory and its rows of the result
+        delivered to pinned host memory, the copies pipelined with the compute:
+
+          * the shard is uploaded straight into this rank's slot of the gathered buffer in COLUMN blocks
+            (``qsb_upload_columns``, copy engine, one flag per block);
+          * two side streams forward every block to the peers as soon as it has landed
+            (``qsb_push_columns_dma``: stream-ordered wait on the upload's flag, 2-D peer copy, flag write on the peer);
+          * the step-1 GEMM is gated on the (source rank x column block) flag grid (``chunk_axis = 2``): tiles of column
+            block j start when block j of the row block they read is there, so the math begins after 1/grid_cols of the
+            transfers instead of after all of them;
+          * the result is produced in row blocks (>= 128 rows each, at most 8); block i travels to the host while block
+            i + 1 is computed.
+
+        ASYNCHRONOUS like ``ApplyMPO``'s host path: ``out_host`` is complete (and ``v_host`` reusable) once the launching
+        stream has reached the end of this call -- synchronise the stream or ``self.host_done``."""
+        if not (v_host.device.type == "cpu" and v_host.is_pinned() and out_host.device.type == "cpu"
+                and out_host.is_pinned()):
+            raise ValueError("forward_host: theta shard and result must be pinned host tensors")
+        ar = self.arena
+        ar.epoch += 1
+        ep, b = ar.epoch, ar.epoch & 1
+        dev = L_rows.device
+        main = torch.cuda.current_stream(dev)
+        h2d, d2h = ar.copy_streams["h2d"], ar.copy_streams["d2h"]
+        nloc = self.chi_l * self.per_row // self.world
+        rows = self.hi - self.lo
+        nc = ar.grid_cols
+        if self.per_row % nc != 0:
+            raise ValueError("forward_host: per_row must be divisible by the number of column blocks")
+        own = self.bufs[b][self.rank * nloc:(self.rank + 1) * nloc]
+        own_flags = ar.grid_flags[self.rank * nc:(self.rank + 1) * nc]
+        start = torch.cuda.Event()
+        start.record(main)               # everything this buffer parity was used for two steps ago is behind `main`
+        h2d.wait_event(start)
+        with torch.cuda.stream(h2d):
+            self._lib.upload_columns(v_host.reshape(-1), own, rows, self.per_row, nc, own_flags, ep)
+        peers = self._order[1:]
+        for si, side in enumerate(ar.side):
+            targets = peers[si::len(ar.side)]
+            if not targets:
+                continue
+            side.wait_event(start)
+            with torch.cuda.stream(side):
+                self._lib.push_columns_dma(own, rows, self.per_row, nc, own_flags,
+                                           [self.dst_ptrs[b][r] for r in targets],
+                                           [ar.grid_flag_ptrs[r] for r in targets], ep)
+        (li, lrow0), (ri, _r0) = self._lib.identity_of(L_rows), self._lib.identity_of(R)
+        per_out = M1.shape[2] * M2.shape[2] * R.shape[1]
+        out_dev = self._host_out(rows * per_out, v_host.dtype, dev)
+        nblk = 1                            # row blocks of >= 128 rows: the last download is all that stays exposed
+        while nblk < 8 and rows % (2 * nblk) == 0 and rows // (2 * nblk) >= 128:
+            nblk *= 2
+        rb = rows // nblk
+        for k in range(nblk):
+            Lb = L_rows[:, k * rb:(k + 1) * rb, :]
+            ob = out_dev[k * rb * per_out:(k + 1) * rb * per_out]
+            self._ops.heff_apply_gridgated(self.bufs[b], Lb, M1, M2, R, ob, ar.grid_flags, self.world, nc, self.rank, ep,
+                                           li, ri, lrow0 + k * rb if li >= 0 else 0)
+            done = torch.cuda.Event()
+            done.record(main)
+            d2h.wait_event(done)
+            with torch.cuda.stream(d2h):
+                out_host[k * rb * per_out:(k + 1) * rb * per_out].copy_(ob, non_blocking=True)
+        for st in (h2d, d2h) + tuple(ar.side):
+            main.wait_stream(st)
+        self.host_done = torch.cuda.Event()
+        self.host_done.record(main)
+        return out_host
+
+    def _host_out(self, n: int, dtype, dev) -> torch.Tensor:
+        buf = getattr(self, "_host_out_buf", None)
+        if buf is None or buf.numel() < n or buf.dtype != dtype:
+            buf = torch.empty(n, dtype=dtype, device=dev)
+            self._host_out_buf = buf
+        return buf[:n]
 
 
 def lanczos_ground_state_sharded(initial_shard: torch.Tensor, linear_operator: Callable,

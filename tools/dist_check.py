@@ -95,6 +95,69 @@ def main():
         t_nccl = timeit(lambda: sop(shard, L_rows, M1, M2, R, out=o2))
     except Exception as ex:
         fused_note = repr(ex)[:300]
+    # host-resident fused matvec (upload in column blocks, block-wise forwarding, grid-gated GEMM, row-block download)
+    host_err, t_host, t_host_serial, host_note = -1.0, 0.0, 0.0, "ok"
+    try:
+        h_in = torch.empty(shard.numel(), dtype=dtype).pin_memory()
+        h_out = torch.empty(out.numel(), dtype=dtype).pin_memory()
+        worst = 0.0
+        for rep in range(5):
+            h_in.copy_((shard * (1.0 + 0.5 * rep)).cpu())
+            if rep == 2:                     # interleave a device-resident call: both flag sets share the epoch counter
+                fop(shard, L_rows, M1, M2, R, out=o2)
+            fop.forward_host(h_in, L_rows, M1, M2, R, h_out)
+            torch.cuda.synchronize()
+            refx = (ref[lo * per_row: hi * per_row] * (1.0 + 0.5 * rep)).cpu()
+            worst = max(worst, float(torch.linalg.norm(h_out - refx) / torch.linalg.norm(refx)))
+            dist.barrier()
+        host_err = worst
+        h_in.copy_(shard.cpu())
+        d_in = torch.empty_like(shard)
+
+        def serial():
+            d_in.copy_(h_in, non_blocking=True)
+            fop(d_in, L_rows, M1, M2, R, out=o2)
+            h_out.copy_(o2, non_blocking=True)
+        t_host = timeit(lambda: fop.forward_host(h_in, L_rows, M1, M2, R, h_out))
+        t_host_serial = timeit(serial)
+    except Exception as ex:
+        host_note = repr(ex)[:300]
+    # two-site split on the row shards against the single-GPU split of the same block
+    split_res = {}
+    try:
+        from quantum_simulation_b200 import svd as qsvd
+        msz = 2 * chi
+        g = torch.Generator(device=dev).manual_seed(17)
+        a = torch.randn(msz, msz, dtype=dtype, device=dev, generator=g)
+        U0 = torch.linalg.qr(a)[0]
+        V0 = torch.linalg.qr(a.T.contiguous())[0]
+        sv = torch.exp(-torch.arange(msz, dtype=torch.float64, device=dev) * (120.0 / msz))
+        th = (U0 * sv.to(dtype)) @ V0.conj().T
+        th = th / torch.linalg.norm(th)
+        dist.broadcast(torch.view_as_real(th) if th.is_complex() else th, src=0)
+        mr = msz // world
+        rows_th = th[rank * mr:(rank + 1) * mr].contiguous()
+        o = qsvd.sketch_split_sharded(rows_th, msz, chi, 0.0, dist.group.WORLD, {})
+        Ug, Sg, Vg, kg = qsvd._gram_split(th, chi, 0.0)
+        if o is None:
+            split_res = {"accepted": False, "rho": qsvd.stats["last_rho"]}
+        else:
+            U, S, Vh, keep = o
+            eye = torch.eye(keep, dtype=dtype, device=dev)
+            t_sh_split = timeit(lambda: qsvd.sketch_split_sharded(rows_th, msz, chi, 0.0, dist.group.WORLD, {}), 5)
+            t_1_split = timeit(lambda: qsvd._sketch_split(th, chi, 0.0), 5)
+            t_g_split = timeit(lambda: qsvd._gram_split(th, chi, 0.0), 5)
+            hsum = torch.tensor([float(U.sum().abs() + Vh.sum().abs() + S.sum())], dtype=torch.float64, device=dev)
+            hmax, hmin = hsum.clone(), hsum.clone()
+            dist.all_reduce(hmax, op=dist.ReduceOp.MAX); dist.all_reduce(hmin, op=dist.ReduceOp.MIN)
+            split_res = {"accepted": True, "rho": qsvd.stats["last_rho"], "keep": keep,
+                         "S2_maxdev_vs_gram": float((S[:keep] ** 2 - Sg[:keep] ** 2).abs().max()),
+                         "iso_dev": [float(torch.linalg.norm(U.conj().T @ U - eye)), float(torch.linalg.norm(Vh @ Vh.conj().T - eye))],
+                         "rec_dev_vs_gram": float(torch.linalg.norm((U * S[:keep].to(dtype)) @ Vh - (Ug * Sg[:keep].to(dtype)) @ Vg)),
+                         "same_on_all_ranks": bool(hmax.item() == hmin.item()),
+                         "ms_sharded": t_sh_split, "ms_single_gpu_sketch": t_1_split, "ms_single_gpu_gram": t_g_split}
+    except Exception as ex:
+        split_res = {"error": repr(ex)[:300]}
     # full sharded DMRG (row-sharded environments, reduce-scatter env updates) vs the single-GPU driver
     import contextlib, io
     import numpy as np
@@ -123,6 +186,12 @@ def main():
     ferr = torch.tensor([fused_err], dtype=torch.float64, device=dev)
     dist.all_reduce(ferr, op=dist.ReduceOp.MAX)
     ok = ok and (fused_note != "ok" or float(ferr) <= 1e-12)
+    herr = torch.tensor([host_err], dtype=torch.float64, device=dev)
+    dist.all_reduce(herr, op=dist.ReduceOp.MAX)
+    host_err = float(herr)
+    ok = ok and (host_note != "ok" or host_err <= 1e-12)
+    if split_res.get("accepted"):
+        ok = ok and split_res["same_on_all_ranks"] and split_res["S2_maxdev_vs_gram"] <= 1e-13 and max(split_res["iso_dev"]) <= 1e-11
     if rank == 0:
         print(json.dumps({"world": world, "chi": chi, "dtype": args.dtype, "matvec_rel_err": float(errs[0]),
                           "lanczos_rel_dev": float(errs[1]), "lanczos_pro_rel_dev": float(errs[2]),
@@ -130,6 +199,8 @@ def main():
                           "lanczos_solve_s_single_gpu": t_1, "dmrg_L20_chi": chi_d,
                           "dmrg_max_rel_dev_per_update": float(errs[3]), "dmrg_bond_dims_equal": bool(errs[4] == 0.0),
                           "dmrg_s_single": t_single, "dmrg_s_sharded": t_shard, "dmrg_comm": d2.comm, "fused_matvec_rel_err": float(ferr),
+                          "host_path_rel_err": host_err, "host_path_ms": t_host, "host_path_serial_ms": t_host_serial,
+                          "host_note": host_note, "sharded_split": split_res,
                           "fused_dma_ms": t_fused, "fused_sm_ms": t_fused_sm, "nccl_ms": t_nccl, "fused_note": fused_note, "ok": ok}))
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
