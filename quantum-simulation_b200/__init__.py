@@ -11,10 +11,15 @@ from . import _lib
 from ._lib import launch_counters, load as load_library
 from .mps import MPS, random_mps
 from .eigensolver import lanczos_ground_state, clear_workspaces
-from .observables import mpo_expectation, energy_expectation, energy_variance
+from .observables import (mpo_expectation, energy_expectation, energy_variance, local_expectation, two_point_correlation,
+                          string_order_parameter, many_body_polarization, structure_factor, correlation_length,
+                          ground_state_fidelity, entanglement_entropy, entanglement_spectrum, product_expectation)
 from .dmrg import (ApplyMPO, LeftEnvUpdate, RightEnvUpdate, EnvironmentManager, Sweeps, DMRG,
                    set_contract_backend)
 
 __all__ = ["MPS", "random_mps", "lanczos_ground_state", "clear_workspaces", "ApplyMPO", "LeftEnvUpdate",
            "RightEnvUpdate", "EnvironmentManager", "Sweeps", "DMRG", "set_contract_backend", "launch_counters",
-           "load_library", "mpo_expectation", "energy_expectation", "energy_variance"]
+           "load_library", "mpo_expectation", "energy_expectation", "energy_variance", "local_expectation",
+           "two_point_correlation", "string_order_parameter", "many_body_polarization", "structure_factor",
+           "correlation_length", "ground_state_fidelity", "entanglement_entropy", "entanglement_spectrum",
+           "product_expectation"]
