@@ -739,11 +739,31 @@ def extras(args, qsb, _lib, dev, dtype, L, M1, M2, R, theta, peak_tf):
         t_l = timed(lambda: qsb.lanczos_ground_state(theta, op, (Ls, M1, M2, Rs), num_restarts=2, krylov_dim=4))
         t_e = timed(lambda: up(Ls, M1, A))
         t_t = timed(lambda: torch.matmul(A.reshape(chi * d, chi), A.reshape(chi, d * chi)))
+        # the split is timed on a block with a DMRG-like Schmidt spectrum (exponential decay: negligible weight beyond
+        # chi, what every bond of a converged sweep looks like -> range-compressed path) and, separately, on the
+        # full-rank random theta of this bench (an unconverged first half-sweep -> the compression is rejected and the
+        # full Gram/eigh path answers)
+        from quantum_simulation_b200 import svd as qsvd
+        m2 = chi * d
+        gsp = torch.Generator(device=dev).manual_seed(11)
+        a_ = torch.randn(m2, m2, dtype=dtype, device=dev, generator=gsp)
+        U0 = torch.linalg.qr(a_)[0]
+        V0 = torch.linalg.qr(a_.T.contiguous())[0]
+        sv = torch.exp(-torch.arange(m2, dtype=torch.float64, device=dev) * (240.0 / m2))
+        th_dmrg = (U0 * sv.to(dtype)) @ V0.conj().T
+        th_dmrg = th_dmrg / torch.linalg.norm(th_dmrg)
+        del a_, U0, V0
+        qsvd._backoff.clear()
+        before = dict(qsvd.stats)
+        t_s = timed(lambda: two_site_split(th_dmrg, chi, 0.0))
+        took_sketch = qsvd.stats["sketch_accepted"] > before["sketch_accepted"]
         th = theta.view(chi * d, d * chi)
-        t_s = timed(lambda: two_site_split(th, chi, 0.0))
+        t_s_full = timed(lambda: two_site_split(th, chi, 0.0, sketch=False))
+        del th_dmrg
         step = t_l + t_e + t_t + t_s
         out["bond_step"] = {"lanczos_8_matvecs_ms": t_l * 1e3, "env_update_ms": t_e * 1e3, "theta_build_ms": t_t * 1e3,
-                            "two_site_split_ms": t_s * 1e3, "total_ms": step * 1e3,
+                            "two_site_split_ms": t_s * 1e3, "two_site_split_path": "range-compressed Gram/eigh" if took_sketch else "full Gram/eigh",
+                            "two_site_split_full_gram_ms": t_s_full * 1e3, "total_ms": step * 1e3,
                             "sweep_estimate_s": 2 * (100 - 1) * step,
                             "note": "bulk bond of Heisenberg L=100 at full chi; a sweep is 198 such steps (edge bonds "
                                     "are cheaper), so sweep_estimate_s is an upper estimate of the sweep time"}
