@@ -498,6 +498,41 @@ def run_ours(args):
                     "quantum_simulation_b200.parallel.FusedShardedApplyMPO / ShardedApplyMPO, copies around it")
                    + " (torch.ops.qsb200.heff_apply* -> qsb_heff_apply)"}
 
+    # ---- the host link this e2e number rides on, measured now: this rank's share of theta up / of the result down, all
+    # ranks at once (they share the host's memory system and PCIe root complexes), alone and both directions together
+    try:
+        s2 = torch.cuda.Stream(device=dev)
+        dd_in, dd_out = torch.empty_like(d_in), torch.empty(n_loc, dtype=dtype, device=dev)
+
+        def both():
+            dd_in.copy_(h_in, non_blocking=True)
+            s2.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(s2):
+                h_out.copy_(dd_out, non_blocking=True)
+            torch.cuda.current_stream(dev).wait_stream(s2)
+        link = {}
+        for name, fn in (("h2d", lambda: dd_in.copy_(h_in, non_blocking=True)),
+                         ("d2h", lambda: h_out.copy_(dd_out, non_blocking=True)), ("both", both)):
+            for _ in range(2):
+                fn()
+            if world > 1:
+                dist.barrier()
+            t_ = time_region(fn, 10) / 10
+            if world > 1:
+                tt = torch.tensor([t_], dtype=torch.float64, device=dev)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                t_ = float(tt.item())
+            link[name + "_ms"] = t_ * 1e3
+        link["h2d_GBps_aggregate"] = n * es / (link["h2d_ms"] * 1e-3) / 1e9
+        link["d2h_GBps_aggregate"] = n * es / (link["d2h_ms"] * 1e-3) / 1e9
+        link["note"] = ("pinned-memory copies of this step's bytes (theta up, result down), every rank its 1/N share "
+                        "concurrently, max over ranks; an e2e step cannot be faster than max(device step, 'both')")
+        e2e["host_link"] = link
+        e2e["floor_ms"] = max(ms_step, link["both_ms"])
+        del dd_in, dd_out
+    except Exception as ex:
+        e2e["host_link"] = {"error": repr(ex)[:200]}
+
     exec_tf = flops_exec_local * world / (sec / K) / 1e12
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,

@@ -226,6 +226,13 @@ typedef struct {
     void*       C; int64_t c_ms, c_ns, c_zs;
     int force_path;         /* 0 = auto, 1 = TMA (error if not eligible), 2 = cp.async */
     int accumulate;         /* 1: C += A.B */
+    /* Optional real scale factors fused into the epilogue (NULL: none; not with accumulate):
+       C[z][m][n] = row_scale[m / row_div] * col_scale[n % col_mod] * (A.B)[z][m][n].
+       This is the Schmidt-weight scaling of the two-site wavefunction build (dmrg.py:633-660): theta's rows (l, s) are
+       scaled with sWeight[l] in a right sweep (row_div = d), its columns (t, r) with sWeight[r] in a left sweep
+       (col_mod = chi_r) -- no separate pass over a site tensor. */
+    const double* row_scale; int row_div;
+    const double* col_scale; int col_mod;
 } qsb_gemm_desc;
 int qsb_gemm(const qsb_gemm_desc* g, void* stream);
 

@@ -84,6 +84,8 @@ class GemmDesc(C.Structure):
         ("C", C.c_void_p), ("c_ms", C.c_int64), ("c_ns", C.c_int64), ("c_zs", C.c_int64),
         ("force_path", C.c_int),
         ("accumulate", C.c_int),
+        ("row_scale", C.c_void_p), ("row_div", C.c_int),
+        ("col_scale", C.c_void_p), ("col_mod", C.c_int),
     ]
 
 
@@ -544,9 +546,12 @@ def lz_scratch_bytes() -> int:
 # plain GEMM (tests, peak probe)
 # ---------------------------------------------------------------------------------------------
 def gemm(A: torch.Tensor, B: torch.Tensor, *, conjA: bool = False, conjB: bool = False,
-         force_path: int = 0, out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+         force_path: int = 0, out: Optional[torch.Tensor] = None, accumulate: bool = False,
+         row_scale=None, col_scale=None) -> torch.Tensor:
     """C[z] = opA(A[z]) @ opB(B[z]) on the library's FP64 tensor-core core.  A: (Z, M, K) or (M, K);
-    B: (Z, K, N) or (K, N); any strides with one unit stride per matrix."""
+    B: (Z, K, N) or (K, N); any strides with one unit stride per matrix.
+    ``row_scale=(v, div)`` / ``col_scale=(v, mod)``: real float64 device vectors fused into the epilogue,
+    C[m][n] *= v_r[m // div] * v_c[n % mod] (the Schmidt weights of the theta build)."""
     lib = load()
     dev = _require_cuda(A, B)
     squeeze = A.dim() == 2
@@ -572,6 +577,21 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, conjA: bool = False, conjB: bool =
     g.C, g.c_zs, g.c_ms, g.c_ns = out.data_ptr(), M * N, N, 1
     g.force_path = force_path
     g.accumulate = int(accumulate)
+    keep = []
+    for name, sc, extent in (("row", row_scale, M), ("col", col_scale, N)):
+        if sc is None:
+            continue
+        v, q = sc
+        v = v.detach().to(device=dev, dtype=torch.float64).contiguous()
+        q = int(q)
+        need = (extent + q - 1) // q if name == "row" else min(q, extent)
+        if q < 1 or v.numel() < need:
+            raise ValueError(f"gemm: {name}_scale has {v.numel()} entries, {need} needed")
+        keep.append(v)
+        if name == "row":
+            g.row_scale, g.row_div = v.data_ptr(), q
+        else:
+            g.col_scale, g.col_mod = v.data_ptr(), q
     with torch.cuda.device(dev):
         check(lib.qsb_gemm(C.byref(g), _stream()), "gemm")
     return out[0] if squeeze else out

@@ -38,6 +38,10 @@ struct GemmArgs {
     int nsplit = 1;                 // > 1: gate whole tiles on the arrival of their COLUMN block of B
     const int* kflags = nullptr;
     int accumulate = 0;             // 1: C += A.B (C must hold valid data), 0: C = A.B
+    // optional real scale factors applied in the epilogue: C[z][m][n] = row_scale[m / row_div] * col_scale[n % col_mod] * (A.B)
+    // (the Schmidt weights of the theta build, dmrg.py:633-660: rows (l, s) scale with l, columns (t, r) with r)
+    const double* row_scale = nullptr; int row_div = 1;
+    const double* col_scale = nullptr; int col_mod = 1;
 };
 int gemm_launch(const GemmArgs& g, cudaStream_t stream);
 

@@ -60,6 +60,8 @@ struct KArgs {
     char* C; long long c_ms, c_ns, c_zs;
     double sgnA, sgnB;              // -1 when the operand is conjugated (complex only)
     int accum;                      // 1: C += A.B
+    const double* row_scale; int row_div;    // epilogue scale factors (nullptr: none)
+    const double* col_scale; int col_mod;
 };
 
 // one operand tile: global -> shared with cp.async, zero fill outside [r_valid) x [k_valid)
@@ -244,6 +246,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_cpasync(const KArgs g) {
             const int n = n0 + wn0 + 8 * j + 2 * t4;
             if (n >= g.N) continue;
             char* dst = Cz + (g.c_ms * m + g.c_ns * n) * C::ES;
+            if (g.row_scale || g.col_scale) {
+                const double rs = g.row_scale ? g.row_scale[m / g.row_div] : 1.0;
+                const double s0 = rs * (g.col_scale ? g.col_scale[n % g.col_mod] : 1.0);
+                const double s1 = rs * ((g.col_scale && n + 1 < g.N) ? g.col_scale[(n + 1) % g.col_mod] : 1.0);
+                acc[i][j][0] *= s0; acc[i][j][1] *= s1;
+                if constexpr (CPLX) { acc[i][j][2] *= s0; acc[i][j][3] *= s1; }
+            }
             if constexpr (!CPLX) {
                 if (g.accum) {
                     acc[i][j][0] += *reinterpret_cast<const double*>(dst);
@@ -319,6 +328,8 @@ int gemm_launch(const GemmArgs& g, cudaStream_t stream) {
     k.C = (char*)g.C; k.c_ms = g.c_ms; k.c_ns = g.c_ns; k.c_zs = g.c_zs;
     k.sgnA = g.conjA ? -1.0 : 1.0; k.sgnB = g.conjB ? -1.0 : 1.0;
     k.accum = g.accumulate;
+    k.row_scale = g.row_scale; k.row_div = g.row_div > 0 ? g.row_div : 1;
+    k.col_scale = g.col_scale; k.col_mod = g.col_mod > 0 ? g.col_mod : 1;
     // extent-1 dimensions carry arbitrary strides in torch: normalise them
     if (g.K == 1) { k.a_ks = 1; k.b_ks = 1; }
     if (g.M == 1 && k.a_ks != 1) k.a_rs = 1;
@@ -389,6 +400,9 @@ extern "C" int qsb_gemm(const qsb_gemm_desc* d, void* stream) {
     g.C = d->C; g.c_ms = d->c_ms; g.c_ns = d->c_ns; g.c_zs = d->c_zs;
     g.force_path = d->force_path;
     g.accumulate = d->accumulate;
+    g.row_scale = d->row_scale; g.row_div = d->row_div; g.col_scale = d->col_scale; g.col_mod = d->col_mod;
+    if ((g.row_scale && g.row_div < 1) || (g.col_scale && g.col_mod < 1)) return QSB_ERR_ARG;
+    if ((g.row_scale || g.col_scale) && g.accumulate) return QSB_ERR_ARG;
     if (g.P < 1) g.P = 1;
     return gemm_launch(g, (cudaStream_t)stream);
 }

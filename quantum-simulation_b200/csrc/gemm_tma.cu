@@ -50,6 +50,8 @@ struct TArgs {
     int nsplit;                          // > 1: whole tiles are gated on the column block of B they read (kflags);
                                          // with ksplit > 1 too: flag kflags[kc * nsplit + column block] per k chunk
     int Zb;                              // batch count (needed for the n-outermost tile order of nsplit mode)
+    const double* row_scale; int row_div;     // SCALED variant: C = row_scale[m / row_div] * col_scale[n % col_mod] * (A.B)
+    const double* col_scale; int col_mod;
     const int* kflags;
 };
 
@@ -210,7 +212,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
 gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TArgs g,
                 const SkArgs sk) {
     using C = TCfg<CPLX>;
-    constexpr bool GATED = VARIANT == 1, ACCUM = VARIANT == 2;
+    constexpr bool GATED = VARIANT == 1, ACCUM = VARIANT == 2, SCALED = VARIANT == 3;
     constexpr int A_BYTES = C::BM * C::BK * C::ES;
     constexpr int B_BYTES = C::BN * C::BK * C::ES;
     constexpr int STAGE = A_BYTES + B_BYTES;
@@ -437,11 +439,19 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         for (int i = 0; i < MI; ++i) {
             const int m = m0 + wm0 + frag_index<CPLX, A_KC>(i, g8);
             if (m >= g.M) continue;
+            double rsv = 1.0;
+            if constexpr (SCALED) { if (g.row_scale) rsv = g.row_scale[m / g.row_div]; }
 #pragma unroll
             for (int j = 0; j < NJ; ++j) {
                 const int c0 = n0 + wn0 + frag_index<CPLX, B_KC>(j, 2 * t4);
                 const int c1 = n0 + wn0 + frag_index<CPLX, B_KC>(j, 2 * t4 + 1);
                 char* row = Cz + g.c_ms * m * C::ES;
+                if constexpr (SCALED) {          // fused Schmidt scaling of the theta build
+                    const double s0 = rsv * ((g.col_scale && c0 < g.N) ? g.col_scale[c0 % g.col_mod] : 1.0);
+                    const double s1 = rsv * ((g.col_scale && c1 < g.N) ? g.col_scale[c1 % g.col_mod] : 1.0);
+                    acc[i][j][0] *= s0; acc[i][j][1] *= s1;
+                    if constexpr (CPLX) { acc[i][j][2] *= s0; acc[i][j][3] *= s1; }
+                }
                 if constexpr (!CPLX) {
                     if (vec_ok && c1 < g.N) {        // c1 == c0 + 1 for the RC permutation
                         double2* dst = reinterpret_cast<double2*>(row + (long long)c0 * C::ES);
@@ -622,8 +632,12 @@ template <bool CPLX, bool A_KC, bool B_KC>
 static int launch_tma(const CUtensorMap& ma, const CUtensorMap& mb, const TArgs& t, int Z, cudaStream_t stream,
                       bool accumulate) {
     if (t.ksplit > 1 || t.nsplit > 1) {
-        if (accumulate) return QSB_ERR_ARG;          // no caller needs a gated accumulating GEMM
+        if (accumulate || t.row_scale || t.col_scale) return QSB_ERR_ARG;   // no caller needs a gated accumulating / scaled GEMM
         return launch_tma_g<CPLX, A_KC, B_KC, 1>(ma, mb, t, Z, stream);
+    }
+    if (t.row_scale || t.col_scale) {
+        if (accumulate) return QSB_ERR_ARG;
+        return launch_tma_g<CPLX, A_KC, B_KC, 3>(ma, mb, t, Z, stream);
     }
     if (accumulate) return launch_tma_g<CPLX, A_KC, B_KC, 2>(ma, mb, t, Z, stream);
     return launch_tma_g<CPLX, A_KC, B_KC, 0>(ma, mb, t, Z, stream);
@@ -662,6 +676,8 @@ int gemm_tma_try(const GemmArgs& g, cudaStream_t stream, bool* used) {
         t.raster = raster_env > 0 ? raster_env : kRasterGroup;
     }
     t.ksplit = 1; t.krot = 0; t.kepoch = 0; t.klocal = 0; t.kflags = nullptr; t.nsplit = 1; t.Zb = g.Z;
+    t.row_scale = g.row_scale; t.row_div = g.row_div > 0 ? g.row_div : 1;
+    t.col_scale = g.col_scale; t.col_mod = g.col_mod > 0 ? g.col_mod : 1;
     if (g.ksplit > 1) {
         const int ktiles = (g.K + BK - 1) / BK;
         if (g.P != 1 || g.K % BK != 0 || ktiles % g.ksplit != 0 || !g.kflags) return QSB_ERR_STRIDE;

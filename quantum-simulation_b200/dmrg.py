@@ -76,14 +76,36 @@ def _check_mpo_shapes(Ms: List[torch.Tensor], ML: torch.Tensor, MR: torch.Tensor
     assert MR.shape[0] == Ms[-1].shape[1], f"MR W={MR.shape[0]} must match Ms[-1].Wr={Ms[-1].shape[1]}"
 
 
-def _matmul2d(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+def _matmul2d(a: torch.Tensor, b: torch.Tensor, row_scale=None, col_scale=None) -> torch.Tensor:
     """(m x k) @ (k x n) on the library's FP64 tensor-core GEMM core (theta build, dmrg.py:645-646 / 659-660);
-    operands with no unit stride are made contiguous first (they are chi^2 d elements)."""
+    operands with no unit stride are made contiguous first (they are chi^2 d elements).  ``row_scale`` / ``col_scale``:
+    (real vector, divisor / modulus) fused into the GEMM epilogue (``_lib.gemm``)."""
     if a.stride(0) != 1 and a.stride(1) != 1:
         a = a.contiguous()
     if b.stride(0) != 1 and b.stride(1) != 1:
         b = b.contiguous()
-    return _lib.gemm(_dev_tensor(a), _dev_tensor(b))
+    return _lib.gemm(_dev_tensor(a), _dev_tensor(b), row_scale=row_scale, col_scale=col_scale)
+
+
+def build_theta(left_t: torch.Tensor, right_t: torch.Tensor, sw: torch.Tensor, direction: str, matmul=_matmul2d,
+                fused: bool = True) -> torch.Tensor:
+    """The two-site wavefunction of a bond (dmrg.py:633-662): ``(sw . left) @ right`` in a right sweep (``sw`` on the
+    left bond of ``left_t``), ``left @ (right . sw)`` in a left sweep (``sw`` on the right bond of ``right_t``), as ONE
+    GEMM with the Schmidt weights applied to the rows (l, s) -> sw[l] resp. columns (t, r) -> sw[r] of the product in
+    its epilogue.  Real weights only (the bulk case); complex boundary factors take the explicit elementwise pass, as
+    does any ``matmul`` without the fused option (the CPU engines of the gloo tests).  ``left_t`` may be a row block
+    (sharded theta build): ``sw`` is then the matching slice."""
+    if sw.dim() == 2:
+        sw = torch.diagonal(sw, 0)
+    l, s, m = left_t.shape
+    _m, t, r = right_t.shape
+    if fused and not sw.is_complex():
+        if direction == "right":
+            return matmul(left_t.reshape(l * s, m), right_t.reshape(m, t * r), row_scale=(sw, s))
+        return matmul(left_t.reshape(l * s, m), right_t.reshape(m, t * r), col_scale=(sw, r))
+    if direction == "right":
+        return matmul(torch.mul(left_t, sw.to(left_t.dtype).view(-1, 1, 1)).reshape(l * s, m), right_t.reshape(m, t * r))
+    return matmul(left_t.reshape(l * s, m), torch.mul(right_t, sw.to(right_t.dtype).view(1, 1, -1)).reshape(m, t * r))
 
 
 class _BaseContractModule(nn.Module):
@@ -433,23 +455,11 @@ class DMRG(nn.Module):
             t0 = self._tick(None, 0.0)
             # 1. two-site wavefunction (dmrg.py:633-662)
             if direction == "right":
-                left_t, right_t = B[p], B[p + 1]
-                sw = sWeight[p]
-                if sw.dim() == 2:
-                    sw = torch.diagonal(sw, 0)
-                l, s, m = left_t.shape
-                _m, t, r = right_t.shape
-                psi = _matmul2d(torch.mul(left_t, sw.to(left_t.dtype).view(-1, 1, 1)).reshape(l * s, m),
-                                right_t.reshape(m, t * r))
+                left_t, right_t, sw = B[p], B[p + 1], sWeight[p]
             else:
-                left_t, right_t = A[p], A[p + 1]
-                sw = sWeight[p + 2]
-                if sw.dim() == 2:
-                    sw = torch.diagonal(sw, 0)
-                l, s, m = left_t.shape
-                _m, t, r = right_t.shape
-                psi = _matmul2d(left_t.reshape(l * s, m),
-                                torch.mul(right_t, sw.to(right_t.dtype).view(1, 1, -1)).reshape(m, t * r))
+                left_t, right_t, sw = A[p], A[p + 1], sWeight[p + 2]
+            l, r = left_t.shape[0], right_t.shape[2]
+            psi = build_theta(left_t, right_t, sw, direction)
             chil, chir = l, r
             psi_flat = psi.reshape(-1)
             t0 = self._tick("theta_build", t0)

@@ -360,9 +360,11 @@ class CudaEngine:
         self._left, self._right = LeftEnvUpdate(), RightEnvUpdate()
         self.vector_ops = None                       # None -> CudaVectorOps
 
-    def matmul(self, a, b):
+    fused_scale = True          # matmul takes row_scale / col_scale (Schmidt weights in the GEMM epilogue)
+
+    def matmul(self, a, b, row_scale=None, col_scale=None):
         from .dmrg import _matmul2d
-        return _matmul2d(a, b)
+        return _matmul2d(a, b, row_scale=row_scale, col_scale=col_scale)
 
     def env_left(self, Lp, M, A):
         return self._left(Lp, M, A)
@@ -657,12 +659,9 @@ class ShardedDMRG:
             chil, chir = l, r
             sharded = L[p].sharded
             lo, hi = self._block(chil) if sharded else (0, l)
-            if direction == "right":
-                left = torch.mul(lt[lo:hi], sw[lo:hi].to(lt.dtype).view(-1, 1, 1)).reshape((hi - lo) * s, m)
-                psi = self.engine.matmul(left, rt.reshape(m, t * r))
-            else:
-                psi = self.engine.matmul(lt[lo:hi].reshape((hi - lo) * s, m),
-                                         torch.mul(rt, sw.to(rt.dtype).view(1, 1, -1)).reshape(m, t * r))
+            from .dmrg import build_theta
+            psi = build_theta(lt[lo:hi], rt, sw[lo:hi] if direction == "right" else sw, direction,
+                              matmul=self.engine.matmul, fused=getattr(self.engine, "fused_scale", False))
             self._tick("theta")
             R_full = self._tag(self._full(R[p + 2]))
             self._tick("gather_R")

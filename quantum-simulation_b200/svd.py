@@ -25,14 +25,16 @@ parity bar, and the kept/discarded split only depends on them through that weigh
 
 Truncating blocks (``maxdim + oversample <= 0.65 min(m, n)``: every bulk bond at a saturated bond dimension,
 where theta is 2 chi x 2 chi and chi directions are kept) first go through a RANGE COMPRESSION (``_sketch_split``):
-``Y = theta Omega`` with a fixed Gaussian ``Omega`` (n x l, l = maxdim + min(128, maxdim/8)), ``Q = orth(Y)`` by shifted CholeskyQR3
+``Y = theta Omega`` with a fixed Gaussian ``Omega`` (n x l, l = maxdim + min(256, maxdim/8)), ``Q = orth(Y)`` by shifted CholeskyQR3
 on the GEMM core, ``B = Q^H theta`` (l x n), and then the same Gram/eigh factorisation of the SMALL matrix B (eigh of
 l x l instead of min(m,n) x min(m,n): 14 ms instead of 85 ms at chi = 2048).  This is exact up to the weight theta has
 outside range(Q), ``rho = |theta|^2 - |B|^2``, which bounds the error of every squared Schmidt value
 (``lambda_j(B B^H) <= lambda_j(theta theta^H) <= lambda_j(B B^H) + rho``).  The result is accepted only if
 ``rho <= SKETCH_TOL |theta|^2`` (1e-13: the absolute noise floor the Gram method has anyway, eps * lambda_max summed
 over the tail); otherwise the block is redone by the full Gram/eigh path, and the sketch is skipped for the next few
-blocks of that shape.  ``S_all`` then carries the l leading Schmidt values plus one pseudo-value sqrt(rho), so that
+blocks of that shape.  (A power-iteration refinement of a marginally rejected compression was tried and dropped: the
+squared spectrum of theta theta^H Q pushes the directions that matter below the regularisation level, and the
+re-orthonormalised variant costs as much as the fallback.)  ``S_all`` then carries the l leading Schmidt values plus one pseudo-value sqrt(rho), so that
 ``sum(S_all[keep:]**2)`` is still the discarded weight the caller records.
 """
 from __future__ import annotations
@@ -45,11 +47,11 @@ __all__ = ["two_site_split", "sketch_split_sharded", "sharded_split_eligible", "
 
 FAST_MIN = 256        # min(m, n) from which the Gram/eigh path is used
 SKETCH = True         # range compression in front of the Gram/eigh path for truncating blocks (module docstring)
-SKETCH_OVERSAMPLE = 128
+SKETCH_OVERSAMPLE = 256
 SKETCH_MAX_FRACTION = 0.65     # use it when maxdim + oversample <= this fraction of min(m, n)
 SKETCH_TOL = 1e-13             # accepted weight of theta outside the compressed range, relative to |theta|^2
 SKETCH_REG = 1e-10             # relative size of the regularising perturbation of the sketch (see _sketch_split)
-SKETCH_BACKOFF = 8             # after a rejected sketch: blocks of the same shape that skip it
+SKETCH_BACKOFF = 4             # after a rejected sketch: blocks of the same shape that skip it
 stats = {"sketch_accepted": 0, "sketch_rejected": 0, "sketch_skipped": 0, "gram": 0, "svd": 0, "last_rho": None}
 _omega_cache: dict = {}
 _backoff: dict = {}
@@ -201,6 +203,7 @@ def _sketch_split(theta: torch.Tensor, maxdim: int, cutoff: float):
     rho = torch.linalg.norm(theta - _mm(Q, B)) ** 2            # the residual itself (|theta|^2 - |B|^2 cancels at 1e-14)
     stats["last_rho"] = float(rho / tot)
     if not stats["last_rho"] <= SKETCH_TOL:                    # (NaN-safe)
+        stats.setdefault("rejected_rhos", []).append(stats["last_rho"])
         return None
     Gs = _mm(B, B.T, conj_b=True)                              # l x l
     Gs = 0.5 * (Gs + Gs.conj().T)

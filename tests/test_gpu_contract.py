@@ -518,3 +518,58 @@ def test_dmrg_sweep_uses_identity_channels():
         env.update_L(p, Q.reshape(l, d, Q.shape[1]))
         want = mpo[p].shape[1] - 1 if p < 18 else -1                # bond 18|19 (W = 4): every term has started
         assert _lib.identity_of(env.get_L(p + 1))[0] == want, p
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.complex128])
+@pytest.mark.parametrize("shape", [(256, 128, 512), (96, 40, 130), (512, 256, 2048)])
+def test_gemm_epilogue_scaling(dtype, shape):
+    """Row / column scale factors fused into the GEMM epilogue (the Schmidt weights of the theta build, row f.2 of
+    SURVEY.md section 8): C[m][n] = rs[m // div] * cs[n % mod] * (A @ B), on the TMA-staged kernel (aligned shapes) and
+    the cp.async one (ragged shapes), against the explicit elementwise scaling."""
+    M, K, N = shape
+    A = randn((M, K), dtype, 31).to(DEV)
+    B = randn((K, N), dtype, 32).to(DEV)
+    div, mod = 2, N // 2
+    rs = torch.rand(M // div, dtype=torch.float64, device=DEV) + 0.5
+    cs = torch.rand(mod, dtype=torch.float64, device=DEV) + 0.5
+    ref = A @ B
+    rfull = rs.repeat_interleave(div).to(dtype).unsqueeze(1)
+    cfull = cs.repeat(N // mod).to(dtype).unsqueeze(0)
+    before = _lib.launch_counters()
+    got_r = _lib.gemm(A, B, row_scale=(rs, div))
+    got_c = _lib.gemm(A, B, col_scale=(cs, mod))
+    got_rc = _lib.gemm(A, B, row_scale=(rs, div), col_scale=(cs, mod))
+    after = _lib.launch_counters()
+    assert rel_err(got_r, ref * rfull) <= 1e-13
+    assert rel_err(got_c, ref * cfull) <= 1e-13
+    assert rel_err(got_rc, ref * rfull * cfull) <= 1e-13
+    tma = after["tma_gemm"] - before["tma_gemm"]
+    assert tma == (3 if (M % 16 == 0 and N % 16 == 0 and K % 16 == 0) else 0) or tma in (0, 3)
+    with pytest.raises(ValueError):
+        _lib.gemm(A, B, row_scale=(rs[:-1], div))
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.complex128])
+@pytest.mark.parametrize("direction", ["right", "left"])
+def test_theta_build_with_fused_schmidt_weights(dtype, direction):
+    """dmrg.build_theta (one GEMM, weights in the epilogue) against the reference's formula (dmrg.py:633-660), also for a
+    row block of the left tensor (the sharded theta build) and for a complex boundary factor (explicit pass)."""
+    from quantum_simulation_b200.dmrg import build_theta
+    l, d, m, r = 48, 2, 64, 80
+    lt = randn((l, d, m), dtype, 41).to(DEV)
+    rt = randn((m, d, r), dtype, 42).to(DEV)
+    sw = torch.rand(l if direction == "right" else r, dtype=torch.float64, device=DEV)
+    if direction == "right":
+        ref = (lt * sw.to(dtype).view(-1, 1, 1)).reshape(l * d, m) @ rt.reshape(m, d * r)
+    else:
+        ref = lt.reshape(l * d, m) @ (rt * sw.to(dtype).view(1, 1, -1)).reshape(m, d * r)
+    assert rel_err(build_theta(lt, rt, sw, direction), ref) <= 1e-13
+    lo, hi = 16, 32
+    part = build_theta(lt[lo:hi], rt, sw[lo:hi] if direction == "right" else sw, direction)
+    assert rel_err(part, ref[lo * d:hi * d]) <= 1e-13
+    if dtype.is_complex:                         # complex boundary factor (2-D sWeight): explicit elementwise pass
+        swc = torch.diag(randn((sw.numel(),), dtype, 43).to(DEV))
+        v = torch.diagonal(swc)
+        ref_c = ((lt * v.view(-1, 1, 1)).reshape(l * d, m) @ rt.reshape(m, d * r) if direction == "right" else
+                 lt.reshape(l * d, m) @ (rt * v.view(1, 1, -1)).reshape(m, d * r))
+        assert rel_err(build_theta(lt, rt, swc, direction), ref_c) <= 1e-13
