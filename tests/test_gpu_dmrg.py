@@ -282,3 +282,42 @@ def test_converged_sweep_energies_config2_full_size():
     mpo = golden_mpo("tfim_c128_L100_g0.5", torch.complex128, DEV)
     assert abs(float(qsb.energy_expectation(dm.mps, mpo)) - E[-1]) < 1e-9
     assert float(qsb.energy_variance(dm.mps, mpo)) < 1e-8
+
+
+# ----------------------------------------------------------------------------- model families of BASELINE configs 4, 5
+def _c45_mpo(z, name, dt):
+    return [torch.from_numpy(z[f"{name}/mpo/t{int(u)}"]).to(dt).contiguous().to(DEV) for u in z[f"{name}/mpo/index"]]
+
+
+@pytest.mark.parametrize("name", ["c4s_j1j2_4x4_f64", "c5s_hubbard_L10_c128"])
+@pytest.mark.parametrize("split", ["default", "gram"])
+def test_dmrg_config4_and_5_model_families(name, split, monkeypatch):
+    """Full DMRG on the MODEL FAMILIES of BASELINE configs 4 and 5 at a size the CPU reference can afford (J1-J2 cylinder
+    4 x 4: FSM MPO bonds up to 26; Fermi-Hubbard via Jordan-Wigner L = 10, d = 4, complex128): every local-update energy
+    within 1e-10 relative of the unmodified reference, same bond dimensions and discarded weights
+    (tests/golden/dmrg_c45.npz, generator make_golden_c45.py)."""
+    from quantum_simulation_b200 import svd as qsvd
+    if split == "gram":
+        monkeypatch.setattr(qsvd, "FAST_MIN", 2)
+    z = load_golden("dmrg_c45")
+    L, d, chi0, seed, ns = (int(x) for x in z[f"{name}/cfg"])
+    dt = torch.complex128 if str(z[f"{name}/dtype"]) == "c128" else torch.float64
+    mps = quiet(qsb.MPS, L, d, chi0, "cpu", dt, seed)
+    sums = np.array([t.detach().abs().sum().item() for t in mps.B])
+    assert np.allclose(sums, z[f"{name}/init_abs_sums"], rtol=1e-13, atol=0)
+    mps = mps.to(DEV)
+    sw = qsb.Sweeps(ns)
+    sw.set_schedule(maxdim=[int(x) for x in z[f"{name}/maxdim"]], krylov_dim=[int(x) for x in z[f"{name}/krylov_dim"]],
+                    cutoff=[float(x) for x in z[f"{name}/cutoff"]], reortho=[bool(x) for x in z[f"{name}/reortho"]],
+                    noise=[0.0] * ns)
+    dm = quiet(qsb.DMRG, mps, _c45_mpo(z, name, dt), device=DEV, dtype=dt)
+    E, _ = quiet(dm, sw, dispon=0, maxit=2)
+    E, Eg = np.array(E), z[f"{name}/energies"]
+    assert len(E) == len(Eg)
+    assert dm.history["bond_dims"] == [int(x) for x in z[f"{name}/bond_dims"]]
+    rel = np.max(np.abs(E - Eg) / np.abs(Eg))
+    assert rel < 1e-10, f"max relative energy deviation {rel:.2e}"
+    if split == "default":
+        assert np.allclose(np.array(dm.history["discarded_weights"]), z[f"{name}/discarded"], rtol=1e-6, atol=1e-12)
+    mpo = _c45_mpo(z, name, dt)
+    assert abs(float(qsb.energy_expectation(dm.mps, mpo)) - E[-1]) < 1e-9

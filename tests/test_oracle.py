@@ -112,3 +112,20 @@ def test_flop_counts():
     chi = 2048
     c3 = 2.0 * (2 * 5 * chi ** 3 * 4 + 2 * 10 * 10 * 2 * chi * chi)
     assert abs(c3 - 6.906e11) / 6.906e11 < 1e-3
+
+
+@pytest.mark.parametrize("name", ["c4s_j1j2_4x4_f64", "c5s_hubbard_L10_c128"])
+def test_oracle_dmrg_config4_and_5_model_families(name):
+    """The oracle's DMRG against the unmodified reference on the model families of BASELINE configs 4 and 5 (small
+    J1-J2 cylinder with wide FSM MPO bonds, Hubbard d = 4 in complex128): tests/golden/dmrg_c45.npz."""
+    z = load_golden("dmrg_c45")
+    L, d, chi0, seed, ns = (int(x) for x in z[f"{name}/cfg"])
+    dt = torch.complex128 if str(z[f"{name}/dtype"]) == "c128" else torch.float64
+    mpo = [torch.from_numpy(z[f"{name}/mpo/t{int(u)}"]).to(dt).contiguous() for u in z[f"{name}/mpo/index"]]
+    mps = orc.OracleMPS(L, d, chi0, dt, seed)
+    E, h = orc.dmrg_run(mps, mpo, numsweeps=ns, maxdim=[int(x) for x in z[f"{name}/maxdim"]],
+                        krylov_dim=[int(x) for x in z[f"{name}/krylov_dim"]], cutoff=[float(x) for x in z[f"{name}/cutoff"]],
+                        reortho=[bool(x) for x in z[f"{name}/reortho"]], maxreortho=[1] * ns)
+    Eg = z[f"{name}/energies"]
+    assert h["bond_dims"] == [int(x) for x in z[f"{name}/bond_dims"]]
+    assert np.max(np.abs(np.array(E) - Eg) / np.abs(Eg)) < 1e-12
