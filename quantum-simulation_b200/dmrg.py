@@ -221,16 +221,23 @@ class ApplyMPO(_BaseContractModule):
         N1 = n_in // chi_li                               # theta as a (chi_l, d1 d2 chi_r) matrix
         # preferred: COLUMN blocks of theta -- an output tile of step 1 needs one block only, so the first tiles start
         # after 1/8 of the upload; fallback: ROW blocks (k chunks), then a plain upload
-        col_chunks = 8
+        col_chunks = 16
         while col_chunks > 1 and (N1 % col_chunks != 0 or (N1 // col_chunks) % bn != 0):
             col_chunks //= 2
         row_chunks = 8
         while row_chunks > 1 and (chi_li % (bk * row_chunks) != 0):
             row_chunks //= 2
         mode = "col" if col_chunks > 1 else ("row" if row_chunks > 1 else "plain")
-        n_blocks = 4
-        while n_blocks > 1 and (chi_lo % n_blocks != 0 or chi_lo // n_blocks < 128):
-            n_blocks //= 2
+        # row blocks of the result: big first, small last (1/2, 1/4, 1/8, 1/8 of the rows while blocks stay >= 128 rows):
+        # every block's download overlaps the next block's compute, only the LAST download is exposed
+        bounds = [0]
+        rest = chi_lo
+        while len(bounds) < 4 and rest % 2 == 0 and rest // 2 >= 128 and rest > 256:
+            bounds.append(bounds[-1] + rest // 2)
+            rest -= rest // 2
+        if rest > 128 and rest % 2 == 0 and len(bounds) >= 2:
+            bounds.append(bounds[-1] + rest // 2)
+        bounds.append(chi_lo)
         main = torch.cuda.current_stream(dev)
         es = psi_host.element_size()
         with torch.cuda.device(dev):
@@ -251,12 +258,11 @@ class ApplyMPO(_BaseContractModule):
                     theta_dev.copy_(psi_host, non_blocking=True)
             if mode == "plain":
                 main.wait_stream(pipe["h2d"])
-            rows = chi_lo // n_blocks
             out_h = out_host.view(-1)
-            for b in range(n_blocks):
-                Lb = L[:, b * rows:(b + 1) * rows, :]
-                ob = out_dev[b * rows * per_out:(b + 1) * rows * per_out]
-                row0 = lrow0 + b * rows                    # an identity channel of L, seen from this row block
+            for r_lo, r_hi in zip(bounds[:-1], bounds[1:]):
+                Lb = L[:, r_lo:r_hi, :]
+                ob = out_dev[r_lo * per_out:r_hi * per_out]
+                row0 = lrow0 + r_lo                        # an identity channel of L, seen from this row block
                 if mode == "col":
                     try:
                         # (the identity shortcut stays valid under gating: the step-1 GEMM of the other channels reads
@@ -281,7 +287,7 @@ class ApplyMPO(_BaseContractModule):
                 done.record(main)
                 pipe["d2h"].wait_event(done)
                 with torch.cuda.stream(pipe["d2h"]):
-                    out_h[b * rows * per_out:(b + 1) * rows * per_out].copy_(ob, non_blocking=True)
+                    out_h[r_lo * per_out:r_hi * per_out].copy_(ob, non_blocking=True)
             pipe["last_mode"] = mode
             main.wait_stream(pipe["d2h"])                  # the result is on the host once `main` gets here
             main.wait_stream(pipe["h2d"])

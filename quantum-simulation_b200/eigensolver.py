@@ -13,7 +13,9 @@ What changed underneath:
     passes per iteration instead of ~17), with alpha/beta/overlaps kept in a device scalar array;
   * the per-iteration ``beta.item()`` host sync (``:263``) is gone: the whole restart is enqueued and alpha/beta
     are read back once; a breakdown (beta_j < beta_tol) is honoured after the fact by truncating the tridiagonal
-    matrix at the same ``j`` the reference would have stopped at, so results are identical;
+    matrix at the same ``j`` the reference would have stopped at, so results are identical.  Only in the converged
+    regime -- after a restart that DID end in a breakdown -- the next restart reads beta back every iteration, so the
+    matvecs the reference skips are skipped here too (a converged sweep applies H_eff twice per bond, not 8 times);
   * the tiny ``k x k`` ``eigh`` (``:285``) runs on the host in float64.
 Control flow stays in Python.  CUDA tensors only -- there is no CPU fallback.
 
@@ -73,6 +75,9 @@ class _Workspace:
         self.OV = 2 * k + 2
         self.scal = torch.zeros(3 * k + 4, 2, device=device, dtype=torch.float64)
         self.scratch = vec.make_scratch(device)
+        # True after a restart that ended in a breakdown (beta_j < beta_tol): the next restart then reads beta back
+        # every iteration, like the reference (:263), and stops at the same j instead of enqueueing all k matvecs
+        self.watch_beta = False
 
 
 _workspaces: Dict[tuple, _Workspace] = {}
@@ -146,6 +151,7 @@ def _lanczos_impl(initial_vector, linear_operator, operator_args, num_restarts, 
             scal.zero_()                                       # alphas, betas <- 0 (:216-222)
             norm_to(ws.best, NRM)                               # vec_cur <- normalize(best_vec) (:214)
             vec.scale(ws.best, K[0], n, scal, NRM)
+            watched_stop = None
             for j in range(k):
                 v = K[j]
                 try:                                            # (:234-238)
@@ -167,6 +173,10 @@ def _lanczos_impl(initial_vector, linear_operator, operator_args, num_restarts, 
                         reduce_sum(scal[OV:OV + j])
                         vec.axpy_norm(K[0], j, n, w, n, scal, OV, 2 * j + 2 if r == reps - 1 else -1, nflag, scratch)
                 finish_norm(2 * j + 2)
+                if ws.watch_beta and j < k - 1:                 # converged regime: stop where the reference stops (:263-265)
+                    if not (float(scal[2 * j + 2, 0].item()) >= beta_tol):
+                        watched_stop = j + 1
+                        break
                 if j < k - 1:                                   # v_{j+1} = w / beta_j (:268-270)
                     vec.scale(w, K[j + 1], n, scal, 2 * j + 2)
 
@@ -174,10 +184,13 @@ def _lanczos_impl(initial_vector, linear_operator, operator_args, num_restarts, 
             alphas = ab[1::2]
             betas = ab[2::2]                                    # beta_0 .. beta_{k-1}
             c = k
-            for j in range(k):                                  # breakdown / last-iteration stop (:263-265)
+            for j in range(k if watched_stop is None else watched_stop):     # breakdown / last-iteration stop (:263-265)
                 if not (float(betas[j]) >= beta_tol) or j == k - 1:
                     c = j + 1
                     break
+            if watched_stop is not None:
+                c = min(c, watched_stop)
+            ws.watch_beta = c < k
             beta_tail = float(betas[c - 1])
             T = torch.zeros(c, c, dtype=torch.float64)
             T.diagonal().copy_(alphas[:c])

@@ -70,3 +70,35 @@ def test_zero_start_vector_restarts_and_tolerances():
     assert abs(E_res - exact) <= 1e-8
     with pytest.raises(ValueError):
         solve(v0, H, krylov_dim=65)
+
+
+def test_converged_regime_stops_where_the_reference_stops():
+    """after a restart that ended in a breakdown the solver watches beta every iteration (like the
+    reference's per-iteration `beta.item()`, lanczos_solver.py:263) and skips the matvecs the reference skips.  An exact
+    eigenvector as start: the first call still enqueues a whole restart (nothing known yet) and learns; the second call
+    applies the operator once per restart -- same energies, same vectors."""
+    from quantum_simulation_b200 import eigensolver
+    H = rand_herm(16, torch.float64, 11)
+    w, V = torch.linalg.eigh(H)
+    calls = {"n": 0}
+
+    def counted(x, A):
+        calls["n"] += 1
+        return A @ x
+    ops = TorchVectorOps()
+
+    def run():
+        calls["n"] = 0
+        v, E = _lanczos_impl(V[:, 0].clone(), counted, (H,), 2, 4, False, 1, 1e-12, None, vec=ops)
+        return v.clone(), E, calls["n"]
+    eigensolver.clear_workspaces()
+    v1, E1, n1 = run()
+    v2, E2, n2 = run()
+    assert abs(E1 - float(w[0])) <= 1e-12 and E2 == E1
+    assert torch.allclose(v1, v2, atol=1e-14)
+    assert n1 == 4 + 1 and n2 == 2          # first restart blind (4), then watched: one matvec per restart
+    # a generic start vector afterwards: beta stays large, the watch switches itself off after one full restart
+    g = torch.Generator().manual_seed(3)
+    calls["n"] = 0
+    _lanczos_impl(torch.randn(16, dtype=torch.float64, generator=g), counted, (H,), 2, 4, False, 1, 1e-12, None, vec=ops)
+    assert calls["n"] == 8
