@@ -153,3 +153,23 @@ def test_sketched_split_rank_deficient_block():
     assert float(torch.linalg.norm((U * S[:keep]) @ Vh - theta)) < 1e-7
     eye = torch.eye(64, dtype=torch.float64)
     assert float(torch.linalg.norm(U.T @ U - eye)) < 1e-12 and float(torch.linalg.norm(Vh @ Vh.T - eye)) < 1e-12
+
+
+@pytest.mark.parametrize("decay", [0.03, 0.05, 0.08])
+def test_cutoff_driven_keep_matches_svd_at_the_default_cutoff(decay, monkeypatch):
+    """the Gram path's eigenvalues carry absolute noise ~eps * lambda_max, the same order as the reference's
+    default cutoff (Sweeps.cutoff = 1e-12) once summed over a long tail.  On graded (DMRG-like) spectra the kept bond
+    dimension and the discarded weight still agree with the SVD path: the noise is per-eigenvalue 1e-16 with random
+    sign, so the tail sum moves by ~sqrt(#tail) * 1e-16 << cutoff.  Both the full and the range-compressed path."""
+    from quantum_simulation_b200 import svd as qsvd
+    for seed in range(4):
+        theta, _ = _matrix(384, 384, torch.float64, decay, seed=seed)
+        theta = theta / torch.linalg.norm(theta)
+        Se = torch.linalg.svdvals(theta)
+        for cutoff in (1e-11, 1e-12, 1e-13):
+            kr = _reference_keep(Se, 10 ** 6, cutoff)
+            for sketch, maxdim in ((False, 10 ** 6), (True, 150)):
+                monkeypatch.setattr(qsvd, "_backoff", {})
+                U, S, Vh, keep = two_site_split(theta, maxdim, cutoff, fast_min=1, sketch=sketch)
+                assert keep == min(kr, maxdim)
+                assert abs(float((S[keep:] ** 2).sum()) - float((Se[keep:] ** 2).sum())) <= 5e-14
