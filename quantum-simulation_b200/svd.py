@@ -32,9 +32,10 @@ outside range(Q), ``rho = |theta|^2 - |B|^2``, which bounds the error of every s
 (``lambda_j(B B^H) <= lambda_j(theta theta^H) <= lambda_j(B B^H) + rho``).  The result is accepted only if
 ``rho <= SKETCH_TOL |theta|^2`` (1e-13: the absolute noise floor the Gram method has anyway, eps * lambda_max summed
 over the tail); otherwise the block is redone by the full Gram/eigh path, and the sketch is skipped for the next few
-blocks of that shape.  (A power-iteration refinement of a marginally rejected compression was tried and dropped: the
-squared spectrum of theta theta^H Q pushes the directions that matter below the regularisation level, and the
-re-orthonormalised variant costs as much as the fallback.)  ``S_all`` then carries the l leading Schmidt values plus one pseudo-value sqrt(rho), so that
+blocks of that shape.  A marginally rejected compression (rho <= 2e-11) first gets one
+step of subspace iteration with re-orthonormalisation (V = orth(B^H), Y <- theta V), which sharpens rho from
+~(1 + maxdim/p) tail to ~tail.  (The plain power step theta theta^H Q was tried and dropped: it squares the spectrum and
+pushes the directions that matter below the regularisation level.)  ``S_all`` then carries the l leading Schmidt values plus one pseudo-value sqrt(rho), so that
 ``sum(S_all[keep:]**2)`` is still the discarded weight the caller records.
 """
 from __future__ import annotations
@@ -51,6 +52,7 @@ SKETCH_OVERSAMPLE = 256
 SKETCH_MAX_FRACTION = 0.65     # use it when maxdim + oversample <= this fraction of min(m, n)
 SKETCH_TOL = 1e-13             # accepted weight of theta outside the compressed range, relative to |theta|^2
 SKETCH_REG = 1e-10             # relative size of the regularising perturbation of the sketch (see _sketch_split)
+SKETCH_REFINE_BELOW = 2e-11    # a rejected compression with rho below this gets one subspace-iteration refinement
 SKETCH_BACKOFF = 4             # after a rejected sketch: blocks of the same shape that skip it
 stats = {"sketch_accepted": 0, "sketch_rejected": 0, "sketch_skipped": 0, "gram": 0, "svd": 0, "last_rho": None}
 _omega_cache: dict = {}
@@ -188,20 +190,37 @@ def _sketch_split(theta: torch.Tensor, maxdim: int, cutoff: float):
     rdt = theta.real.dtype if theta.is_complex() else theta.dtype
     Y = _mm(theta, _omega(n, l, theta.dtype, theta.device))    # m x l
     # DMRG blocks are numerically rank-deficient (Schmidt values far below eps), which no Cholesky-based
-    # orthogonalisation survives: lift the null directions of Y to SKETCH_REG |Y| with a fixed Gaussian perturbation.
-    # range(Q) then contains the resolved directions of range(Y) up to angles ~SKETCH_REG / sigma_i, which costs
-    # ~rank * SKETCH_REG^2 of captured weight (1e-17 at 1e-10) -- measured by rho below like everything else.
-    if SKETCH_REG > 0:
-        Y.add_(_fixed_normal("reg", m, l, theta.dtype, theta.device, 0xB200),
-               alpha=float(SKETCH_REG * torch.linalg.norm(Y)) / (m * l) ** 0.5)
-    Q = _orthonormal_cols(Y)
-    if Q is None:
-        stats["householder"] = stats.get("householder", 0) + 1
-        Q = torch.linalg.qr(Y)[0]
-    B = _mm(Q.T, theta, conj_a=True)                           # l x n
+    # orthogonalisation survives: `orth` lifts the null directions of Y to SKETCH_REG |Y| with a fixed Gaussian
+    # perturbation.  range(Q) then contains the resolved directions of range(Y) up to angles ~SKETCH_REG / sigma_i, which
+    # costs ~rank * SKETCH_REG^2 of captured weight (1e-17 at 1e-10) -- measured by rho like everything else.
     tot = torch.linalg.norm(theta) ** 2
-    rho = torch.linalg.norm(theta - _mm(Q, B)) ** 2            # the residual itself (|theta|^2 - |B|^2 cancels at 1e-14)
+
+    def orth(Yc, tag):
+        """Regularised shifted CholeskyQR of a tall matrix (Householder QR when a Cholesky pivot fails)."""
+        if SKETCH_REG > 0:
+            Yc.add_(_fixed_normal(tag, Yc.shape[0], Yc.shape[1], theta.dtype, theta.device, 0xB200),
+                    alpha=float(SKETCH_REG * torch.linalg.norm(Yc)) / (Yc.shape[0] * Yc.shape[1]) ** 0.5)
+        Qc = _orthonormal_cols(Yc)
+        if Qc is None:
+            stats["householder"] = stats.get("householder", 0) + 1
+            Qc = torch.linalg.qr(Yc)[0]
+        return Qc
+
+    def compress(Yc):
+        """Q = orth(Yc), B = Q^H theta and the weight of theta outside range(Q)."""
+        Qc = orth(Yc, "reg")
+        Bc = _mm(Qc.T, theta, conj_a=True)                     # l x n
+        return Qc, Bc, torch.linalg.norm(theta - _mm(Qc, Bc)) ** 2      # (|theta|^2 - |B|^2 would cancel at 1e-14)
+    Q, B, rho = compress(Y)
     stats["last_rho"] = float(rho / tot)
+    if SKETCH_TOL < stats["last_rho"] <= SKETCH_REFINE_BELOW:
+        # marginal miss: one step of subspace iteration WITH re-orthonormalisation (V = orth(B^H), Y <- theta V): the
+        # captured range sharpens from ~(1 + k/p) tail to ~tail at the cost of two more orthonormalisations -- still
+        # cheaper than the full eigenproblem, much cheaper than the gathered fallback of the sharded driver
+        stats["sketch_refined"] = stats.get("sketch_refined", 0) + 1
+        V1 = orth(B.conj().T.contiguous() if theta.is_complex() else B.T.contiguous(), "reg2")      # n x l
+        Q, B, rho = compress(_mm(theta, V1))
+        stats["last_rho"] = float(rho / tot)
     if not stats["last_rho"] <= SKETCH_TOL:                    # (NaN-safe)
         stats.setdefault("rejected_rhos", []).append(stats["last_rho"])
         return None
@@ -284,20 +303,43 @@ def sketch_split_sharded(theta_rows: torch.Tensor, m: int, maxdim: int, cutoff: 
         return None
 
     Y = _mm(theta_rows, _omega(n, l, dt, dev))
-    if SKETCH_REG > 0:
-        ny = (torch.linalg.norm(Y) ** 2).reshape(1)
-        allsum(ny)
-        reg = _fixed_normal("reg", m, l, dt, dev, 0xB200)[rank * mr:(rank + 1) * mr]
-        Y.add_(reg, alpha=float(SKETCH_REG * torch.sqrt(ny)) / (m * l) ** 0.5)
-    Q = _orthonormal_cols(Y, m_total=m, allsum=allsum, agree=agree)
+
+    def regularise(Yc, tag, rows_total, r0):
+        if SKETCH_REG > 0:
+            ny = (torch.linalg.norm(Yc) ** 2).reshape(1)
+            allsum(ny)
+            reg = _fixed_normal(tag, rows_total, l, dt, dev, 0xB200)[r0:r0 + Yc.shape[0]]
+            Yc.add_(reg, alpha=float(SKETCH_REG * torch.sqrt(ny)) / (rows_total * l) ** 0.5)
+        return Yc
+
+    def compress(Yc):
+        Qc = _orthonormal_cols(regularise(Yc, "reg", m, rank * mr), m_total=m, allsum=allsum, agree=agree)
+        if Qc is None:
+            return None, None, None
+        Bc_ = _mm(Qc.T, theta_rows, conj_a=True)               # partial l x n
+        allsum(Bc_)
+        w_ = torch.stack([torch.linalg.norm(theta_rows - _mm(Qc, Bc_)) ** 2, torch.linalg.norm(theta_rows) ** 2])
+        allsum(w_)
+        return Qc, Bc_, w_
+    Q, B, w = compress(Y)
     if Q is None:
         return reject()
-    B = _mm(Q.T, theta_rows, conj_a=True)                      # partial l x n
-    allsum(B)
-    w = torch.stack([torch.linalg.norm(theta_rows - _mm(Q, B)) ** 2, torch.linalg.norm(theta_rows) ** 2])
-    allsum(w)
-    rho, tot = w[0], w[1]
-    stats["last_rho"] = float(rho / tot)
+    stats["last_rho"] = float(w[0] / w[1])
+    if SKETCH_TOL < stats["last_rho"] <= SKETCH_REFINE_BELOW:  # one decision for all ranks (all-reduced rho)
+        # subspace-iteration refinement, see _sketch_split: V = orth(B^H) with the rows of B^H (columns of theta) sharded
+        stats["sketch_refined"] = stats.get("sketch_refined", 0) + 1
+        Bh = B[:, c0:c0 + nc]
+        Bh = (Bh.conj().T if B.is_complex() else Bh.T).contiguous()           # this rank's nc rows of B^H (n x l)
+        Vc = _orthonormal_cols(regularise(Bh, "reg2", n, c0), m_total=n, allsum=allsum, agree=agree)
+        if Vc is None:
+            return reject()
+        V1 = torch.empty(n, l, dtype=dt, device=dev)
+        dist.all_gather_into_tensor(V1.view(-1), Vc.contiguous().view(-1), group=group)
+        Q, B, w = compress(_mm(theta_rows, V1))
+        if Q is None:
+            return reject()
+        stats["last_rho"] = float(w[0] / w[1])
+    rho = w[0]
     if not stats["last_rho"] <= SKETCH_TOL:
         return reject()
     Bc = B[:, c0:c0 + nc]

@@ -173,3 +173,21 @@ def test_cutoff_driven_keep_matches_svd_at_the_default_cutoff(decay, monkeypatch
                 U, S, Vh, keep = two_site_split(theta, maxdim, cutoff, fast_min=1, sketch=sketch)
                 assert keep == min(kr, maxdim)
                 assert abs(float((S[keep:] ** 2).sum()) - float((Se[keep:] ** 2).sum())) <= 5e-14
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.complex128])
+def test_sketched_split_refines_a_marginal_miss(dtype, monkeypatch):
+    """rho of the plain compression a few times above the bound: one subspace-iteration step with re-orthonormalisation
+    brings it to ~1.6 x the weight beyond the compressed dimension, and the block is accepted."""
+    from quantum_simulation_b200 import svd as qsvd
+    monkeypatch.setattr(qsvd, "_backoff", {})
+    theta, _ = _matrix(256, 256, dtype, 0.2, seed=1)
+    theta = theta / torch.linalg.norm(theta)
+    before = dict(qsvd.stats)
+    U, S, Vh, keep = two_site_split(theta, 64, 0.0, fast_min=1)
+    assert qsvd.stats.get("sketch_refined", 0) == before.get("sketch_refined", 0) + 1
+    assert qsvd.stats["sketch_accepted"] == before["sketch_accepted"] + 1 and qsvd.stats["last_rho"] <= 1e-13
+    Se = torch.linalg.svdvals(theta)
+    assert float((S[:64] ** 2 - Se[:64] ** 2).abs().max()) <= 2e-13
+    eye = torch.eye(64, dtype=dtype)
+    assert float(torch.linalg.norm(U.conj().T @ U - eye)) < 1e-12 and float(torch.linalg.norm(Vh @ Vh.conj().T - eye)) < 1e-12
