@@ -32,9 +32,9 @@ outside range(Q), ``rho = |theta|^2 - |B|^2``, which bounds the error of every s
 (``lambda_j(B B^H) <= lambda_j(theta theta^H) <= lambda_j(B B^H) + rho``).  The result is accepted only if
 ``rho <= SKETCH_TOL |theta|^2`` (1e-13: the absolute noise floor the Gram method has anyway, eps * lambda_max summed
 over the tail); otherwise the block is redone by the full Gram/eigh path, and the sketch is skipped for the next few
-blocks of that shape.  A marginally rejected compression (rho <= 2e-11) first gets one
-step of subspace iteration with re-orthonormalisation (V = orth(B^H), Y <- theta V), which sharpens rho from
-~(1 + maxdim/p) tail to ~tail.  (The plain power step theta theta^H Q was tried and dropped: it squares the spectrum and
+blocks of that shape.  On row shards (and optionally on one GPU, ``SKETCH_REFINE_SINGLE``) a
+marginally rejected compression (rho <= 2e-11) first gets one step of subspace iteration with re-orthonormalisation
+(V = orth(B^H), Y <- theta V), which sharpens rho from ~50 x to ~1.6 x the weight beyond the compressed dimension.  (The plain power step theta theta^H Q was tried and dropped: it squares the spectrum and
 pushes the directions that matter below the regularisation level.)  ``S_all`` then carries the l leading Schmidt values plus one pseudo-value sqrt(rho), so that
 ``sum(S_all[keep:]**2)`` is still the discarded weight the caller records.
 """
@@ -52,7 +52,9 @@ SKETCH_OVERSAMPLE = 256
 SKETCH_MAX_FRACTION = 0.65     # use it when maxdim + oversample <= this fraction of min(m, n)
 SKETCH_TOL = 1e-13             # accepted weight of theta outside the compressed range, relative to |theta|^2
 SKETCH_REG = 1e-10             # relative size of the regularising perturbation of the sketch (see _sketch_split)
-SKETCH_REFINE_BELOW = 2e-11    # a rejected compression with rho below this gets one subspace-iteration refinement
+SKETCH_REFINE_BELOW = 2e-11    # a rejected compression with rho below this gets one subspace-iteration refinement ...
+SKETCH_REFINE_SINGLE = False   # ... on row shards always (the gathered rank-0 fallback costs 3x more); on one GPU it
+                               # measured as a wash against falling back (C3 sweep 36.4 -> 38.7 s with it), so it is off
 SKETCH_BACKOFF = 4             # after a rejected sketch: blocks of the same shape that skip it
 stats = {"sketch_accepted": 0, "sketch_rejected": 0, "sketch_skipped": 0, "gram": 0, "svd": 0, "last_rho": None}
 _omega_cache: dict = {}
@@ -213,7 +215,7 @@ def _sketch_split(theta: torch.Tensor, maxdim: int, cutoff: float):
         return Qc, Bc, torch.linalg.norm(theta - _mm(Qc, Bc)) ** 2      # (|theta|^2 - |B|^2 would cancel at 1e-14)
     Q, B, rho = compress(Y)
     stats["last_rho"] = float(rho / tot)
-    if SKETCH_TOL < stats["last_rho"] <= SKETCH_REFINE_BELOW:
+    if SKETCH_REFINE_SINGLE and SKETCH_TOL < stats["last_rho"] <= SKETCH_REFINE_BELOW:
         # marginal miss: one step of subspace iteration WITH re-orthonormalisation (V = orth(B^H), Y <- theta V): the
         # captured range sharpens from ~(1 + k/p) tail to ~tail at the cost of two more orthonormalisations -- still
         # cheaper than the full eigenproblem, much cheaper than the gathered fallback of the sharded driver

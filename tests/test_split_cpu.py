@@ -181,6 +181,7 @@ def test_sketched_split_refines_a_marginal_miss(dtype, monkeypatch):
     brings it to ~1.6 x the weight beyond the compressed dimension, and the block is accepted."""
     from quantum_simulation_b200 import svd as qsvd
     monkeypatch.setattr(qsvd, "_backoff", {})
+    monkeypatch.setattr(qsvd, "SKETCH_REFINE_SINGLE", True)
     theta, _ = _matrix(256, 256, dtype, 0.2, seed=1)
     theta = theta / torch.linalg.norm(theta)
     before = dict(qsvd.stats)
