@@ -485,8 +485,19 @@ def run_ours(args):
         t = torch.tensor([sec_e], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         sec_e = float(t.item())
+    # how long the HOST needs to enqueue one such step (no device synchronisation inside): if this approaches ms_per_step
+    # the e2e number is launch-bound, not copy- or compute-bound
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        step_e2e()
+    enqueue_ms = (time.perf_counter() - t0) / 3 * 1e3
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     e2e = {"value": flops_total / (sec_e / Ke) / 1e9, "unit": UNIT, "h2d_bytes_per_step": n * es,
            "d2h_bytes_per_step": n * es, "ms_per_step": sec_e / Ke * 1e3, "steps": Ke,
+           "host_enqueue_ms_per_step": enqueue_ms,
            "bytes_note": "whole-job bytes per step, summed over ranks (each rank moves 1/N of them)",
            "host_pipeline_mode": (next(iter(qsb.ApplyMPO._host_pipes.values()), {}).get("last_mode")
                                   if world == 1 else e2e_mode),

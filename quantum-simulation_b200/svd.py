@@ -51,7 +51,7 @@ SKETCH = True         # range compression in front of the Gram/eigh path for tru
 SKETCH_OVERSAMPLE = 256
 SKETCH_MAX_FRACTION = 0.65     # use it when maxdim + oversample <= this fraction of min(m, n)
 SKETCH_TOL = 1e-13             # accepted weight of theta outside the compressed range, relative to |theta|^2
-SKETCH_REG = 1e-10             # relative size of the regularising perturbation of the sketch (see _sketch_split)
+SKETCH_REG = 1e-9              # relative size of the regularising perturbation of the sketch (see _sketch_split)
 SKETCH_REFINE_BELOW = 2e-11    # a rejected compression with rho below this gets one subspace-iteration refinement ...
 SKETCH_REFINE_SINGLE = False   # ... on row shards always (the gathered rank-0 fallback costs 3x more); on one GPU it
                                # measured as a wash against falling back (C3 sweep 36.4 -> 38.7 s with it), so it is off
@@ -126,7 +126,7 @@ def _orthonormal_rows(B: torch.Tensor, allsum=None, agree=None):
     return X
 
 
-def _orthonormal_cols(Y: torch.Tensor, shifted_passes: int = 2, *, m_total: int = None, allsum=None, agree=None):
+def _orthonormal_cols(Y: torch.Tensor, shifted_passes: int = 1, *, m_total: int = None, allsum=None, agree=None):
     """Orthonormal basis of range(Y) for a tall, ill-conditioned Y (m x l): shifted CholeskyQR (Fukaya et al.):
     ``shifted_passes`` Cholesky passes on G + s I with s = 11 (m l + l (l + 1)) eps |Y|_2^2 (each divides the
     condition number by ~1e4 until it is below 1/sqrt(eps)), then CholeskyQR2 -- Gram GEMMs on the library's core,
@@ -194,7 +194,7 @@ def _sketch_split(theta: torch.Tensor, maxdim: int, cutoff: float):
     # DMRG blocks are numerically rank-deficient (Schmidt values far below eps), which no Cholesky-based
     # orthogonalisation survives: `orth` lifts the null directions of Y to SKETCH_REG |Y| with a fixed Gaussian
     # perturbation.  range(Q) then contains the resolved directions of range(Y) up to angles ~SKETCH_REG / sigma_i, which
-    # costs ~rank * SKETCH_REG^2 of captured weight (1e-17 at 1e-10) -- measured by rho like everything else.
+    # costs ~rank * SKETCH_REG^2 of captured weight (1e-19 measured at 1e-9) -- measured by rho like everything else.
     tot = torch.linalg.norm(theta) ** 2
 
     def orth(Yc, tag):

@@ -180,6 +180,39 @@ def case_c3full():
              "discarded_weight_max_full_chi": float(max(w for w, b in zip(dm.history["discarded_weights"], bd) if b == 2048))}]
 
 
+def case_c3multi(nsweeps=3):
+    """BASELINE config 3, several sweeps: the time and the end-of-sweep energy of every sweep (the first one starts from
+    the random state, later ones are in the converged regime: every split takes the range-compressed path and the
+    Lanczos solver stops where the reference stops)."""
+    import quantum_simulation_b200.svd as _qsvd
+    dt = torch.float64
+    mps = quiet(qsb.MPS, 100, 2, 2048, DEV, dt, 1)
+    mpo_ = [m.to(DEV) for m in mpo("heis_f64_L100", dt)]
+    dm = quiet(qsb.DMRG, mps, mpo_, device=DEV, dtype=dt)
+    torch.manual_seed(1)
+    rows = []
+    for k in range(nsweeps):
+        sw = qsb.Sweeps(1)
+        sw.set_schedule(maxdim=[2048], cutoff=[0.0], krylov_dim=[4], noise=[0.0])
+        before = dict(_qsvd.stats)
+        lc0 = qsb.launch_counters()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        E, _ = quiet(dm, sw, dispon=0, maxit=2)
+        torch.cuda.synchronize()
+        t = time.perf_counter() - t0
+        lc1 = qsb.launch_counters()
+        rows.append({"case": f"C3 Heisenberg L=100 chi=2048 f64, sweep {k + 1} of {nsweeps} on the same state", "sweep_s": t,
+                     "E_end_of_sweep": float(E[-1]),
+                     "split_paths": {key: _qsvd.stats[key] - before.get(key, 0) for key in
+                                     ("sketch_accepted", "sketch_rejected", "sketch_skipped", "gram", "svd")},
+                     "gemm_launches": lc1["tma_gemm"] - lc0["tma_gemm"],
+                     "discarded_weight_max": float(max(dm.history["discarded_weights"]))})
+    rows.append({"case": "C3 after the last sweep", "E_by_environments": float(qsb.energy_expectation(dm.mps, mpo_)),
+                 "variance_by_environments": float(qsb.energy_variance(dm.mps, mpo_))})
+    return rows
+
+
 def case_split():
     """Stage timing of the two-site split at the C3 bulk shape (4096 x 4096 float64, keep 2048) on a block with a
     DMRG-like spectrum: the range-compressed path against the full Gram/eigh path."""
@@ -249,5 +282,5 @@ def case_split():
 if __name__ == "__main__":
     which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["c1"]
     for w in which:
-        for row in {"c1": case_c1, "c2": case_c2, "c3": case_c3, "svd": case_svd, "c3full": case_c3full, "split": case_split}[w]():
+        for row in {"c1": case_c1, "c2": case_c2, "c3": case_c3, "svd": case_svd, "c3full": case_c3full, "split": case_split, "c3multi": case_c3multi}[w]():
             print(json.dumps(row), flush=True)

@@ -60,11 +60,11 @@ def test_gram_split_rank_deficient_and_degenerate(monkeypatch):
 
 
 def test_sketched_split_rank_deficient_and_degenerate(monkeypatch):
-    """Same blocks through the range compression: reconstruction to the regularisation amplitude (1e-10 relative)."""
+    """Same blocks through the range compression: reconstruction to the regularisation amplitude (1e-9 relative)."""
     from quantum_simulation_b200 import svd as qsvd
     monkeypatch.setattr(qsvd, "_backoff", {})
     before = qsvd.stats["sketch_accepted"]
-    _rank_deficient_and_degenerate(1e-9)
+    _rank_deficient_and_degenerate(5e-9)
     assert qsvd.stats["sketch_accepted"] >= before + 2
 
 
