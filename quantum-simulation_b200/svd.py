@@ -126,37 +126,54 @@ def _orthonormal_rows(B: torch.Tensor, allsum=None, agree=None):
     return X
 
 
-def _orthonormal_cols(Y: torch.Tensor, shifted_passes: int = 1, *, m_total: int = None, allsum=None, agree=None):
-    """Orthonormal basis of range(Y) for a tall, ill-conditioned Y (m x l): shifted CholeskyQR (Fukaya et al.):
-    ``shifted_passes`` Cholesky passes on G + s I with s = 11 (m l + l (l + 1)) eps |Y|_2^2 (each divides the
-    condition number by ~1e4 until it is below 1/sqrt(eps)), then CholeskyQR2 -- Gram GEMMs on the library's core,
-    l x l Cholesky factorisations and triangular solves.  None if a factorisation breaks down or the last pass does
-    not start from a nearly orthonormal matrix (the caller then uses Householder QR).
+def _orthonormal_cols(Y: torch.Tensor, max_passes: int = 6, *, m_total: int = None, allsum=None, agree=None):
+    """Orthonormal basis of range(Y) for a tall, ill-conditioned Y (m x l) by adaptive shifted CholeskyQR (Fukaya et
+    al.): every pass forms the Gram matrix G = X^H X (GEMM on the library's core), factors it and solves X <- X L^-H.
+    The first pass -- and any later pass whose plain Cholesky factorisation breaks down -- adds the shift
+    s = 11 (m l + l (l + 1)) eps trace(G), which divides the condition number by ~1e4 per pass; as soon as G is within
+    1e-2 of the identity one last plain pass makes X orthonormal to O(eps).  Typically 1 shifted + 2 plain passes at the
+    regularisation used by the callers, one more shifted pass for harder spectra.  None if ``max_passes`` do not get
+    there (the caller then uses Householder QR).
     Row-sharded use: ``Y`` is this rank's row block of an ``m_total`` x l matrix; ``allsum`` / ``agree`` as in
-    ``_orthonormal_rows`` (the l x l Gram matrices are summed over the ranks, the Cholesky factorisations replicated)."""
+    ``_orthonormal_rows`` (the l x l Gram matrices are summed over the ranks, the Cholesky factorisations replicated,
+    every branch is decided from all-reduced data)."""
     m, l = Y.shape
     m = m if m_total is None else int(m_total)
     eps = torch.finfo(Y.real.dtype if Y.is_complex() else Y.dtype).eps
+    eye = None
     X = Y
-    total = shifted_passes + 2
-    for it in range(total):
+    shifted = True
+    it = 0
+    while it < max_passes:
         Gm = _mm(X.T, X, conj_a=True)                         # l x l
         if allsum is not None:
             allsum(Gm)
         Gm = 0.5 * (Gm + Gm.conj().T)
-        bad = False
-        if it < shifted_passes:
-            shift = 11.0 * (m * l + l * (l + 1)) * eps * torch.diagonal(Gm).real.sum()   # trace >= |X|_2^2
-            Gm.diagonal().add_(shift.to(Gm.dtype))
-        elif it == total - 1:   # Gram matrix of the previous pass's output: the last pass is orthonormal to O(eps)
-            dev_ = Gm - torch.eye(l, dtype=Gm.dtype, device=Gm.device)        # iff this is already close to I
-            bad = not float(dev_.abs().max()) < 1e-2
-        Lc, info = torch.linalg.cholesky_ex(Gm)
-        bad = bad or int(info) != 0
+        if it > 0:
+            if eye is None:
+                eye = torch.eye(l, dtype=Gm.dtype, device=Gm.device)
+            if float((Gm - eye).abs().max()) < 1e-2:          # last pass: plain Cholesky of a matrix close to I
+                Lc, info = torch.linalg.cholesky_ex(Gm)
+                bad = int(info) != 0
+                if agree(bad) if agree is not None else bad:
+                    return None
+                return torch.linalg.solve_triangular(Lc.conj().T, X, upper=True, left=False)
+        G2 = Gm
+        if shifted:
+            G2 = Gm.clone()
+            G2.diagonal().add_((11.0 * (m * l + l * (l + 1)) * eps * torch.diagonal(Gm).real.sum()).to(Gm.dtype))
+        Lc, info = torch.linalg.cholesky_ex(G2)
+        bad = int(info) != 0
         if agree(bad) if agree is not None else bad:
-            return None
+            if shifted:
+                return None                                    # not even the shifted matrix is positive definite
+            shifted = True                                     # redo this pass with the shift (X unchanged)
+            it += 1
+            continue
         X = torch.linalg.solve_triangular(Lc.conj().T, X, upper=True, left=False)     # X <- X Lc^{-H}
-    return X
+        shifted = False
+        it += 1
+    return None
 
 
 def _omega(n: int, l: int, dtype: torch.dtype, device: torch.device) -> torch.Tensor:

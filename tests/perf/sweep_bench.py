@@ -245,7 +245,7 @@ def case_split():
         regs = {}
         for reg in (1e-9, 1e-10, 1e-11, 1e-12):
             Yr = Y + qsvd._fixed_normal("reg", n, l, dt, theta.device, 0xB200) * (reg * float(torch.linalg.norm(Y)) / (n * l) ** 0.5)
-            for sp in (1, 2, 3):
+            for sp in (6,):
                 t_, Qr = tm(lambda: qsvd._orthonormal_cols(Yr, sp), 1)
                 if Qr is not None:
                     regs[f"reg{reg:g}_passes{sp}"] = {"ms": t_, "rho": float(torch.linalg.norm(theta - Qr @ (Qr.T @ theta)) ** 2),
@@ -264,6 +264,7 @@ def case_split():
         Bk = B[:k].contiguous()
         t_o, _ = tm(lambda: qsvd._orthonormal_rows(Bk))
         row = {"case": f"two-site split 4096x4096 f64 keep 2048, S_j ~ exp(-{decay * 8 / n:.3f} j)", "gram_split_ms": t_gram,
+               "stats": {k_: v_ for k_, v_ in qsvd.stats.items() if k_ != "rejected_rhos"},
                "sketch_split_ms": t_sk, "sketch_accepted": out is not None, "rho": qsvd.stats["last_rho"],
                "stages_ms": {"Y=theta*Omega": t_y, "sCholQR3(Y)": t_q, "cholqr_ok": qsvd._orthonormal_cols(Y) is not None,
                              "householder_qr(Y)": t_hq, "B=Q^H theta": t_b, "residual": t_r, f"eigh({l})": t_e,
