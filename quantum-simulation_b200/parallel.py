@@ -260,8 +260,8 @@ class FusedShardedApplyMPO:
           * the step-1 GEMM is gated on the (source rank x column block) flag grid (``chunk_axis = 2``): tiles of column
             block j start when block j of the row block they read is there, so the math begins after 1/grid_cols of the
             transfers instead of after all of them;
-          * the result is produced in row blocks (>= 128 rows each, at most 8); block i travels to the host while block
-            i + 1 is computed.
+          * the result is produced in row blocks (1/2, 1/4, ... of the rows, >= 128 each); block i travels to the host
+            while block i + 1 is computed.
 
         ASYNCHRONOUS like ``ApplyMPO``'s host path: ``out_host`` is complete (and ``v_host`` reusable) once the launching
         stream has reached the end of this call -- synchronise the stream or ``self.host_done``."""
@@ -299,20 +299,26 @@ class FusedShardedApplyMPO:
         (li, lrow0), (ri, _r0) = self._lib.identity_of(L_rows), self._lib.identity_of(R)
         per_out = M1.shape[2] * M2.shape[2] * R.shape[1]
         out_dev = self._host_out(rows * per_out, v_host.dtype, dev)
-        nblk = 1                            # row blocks of >= 128 rows: the last download is all that stays exposed
-        while nblk < 8 and rows % (2 * nblk) == 0 and rows // (2 * nblk) >= 128:
-            nblk *= 2
-        rb = rows // nblk
-        for k in range(nblk):
-            Lb = L_rows[:, k * rb:(k + 1) * rb, :]
-            ob = out_dev[k * rb * per_out:(k + 1) * rb * per_out]
+        # row blocks of the result, big first, small last (1/2, 1/4, ... while blocks stay >= 128 rows): every block's
+        # download overlaps the next block's compute and only the last, smallest download stays exposed
+        bounds = [0]
+        rest = rows
+        while len(bounds) < 4 and rest % 2 == 0 and rest // 2 >= 128 and rest > 256:
+            bounds.append(bounds[-1] + rest // 2)
+            rest -= rest // 2
+        if rest > 128 and rest % 2 == 0:
+            bounds.append(bounds[-1] + rest // 2)
+        bounds.append(rows)
+        for r_lo, r_hi in zip(bounds[:-1], bounds[1:]):
+            Lb = L_rows[:, r_lo:r_hi, :]
+            ob = out_dev[r_lo * per_out:r_hi * per_out]
             self._ops.heff_apply_gridgated(self.bufs[b], Lb, M1, M2, R, ob, ar.grid_flags, self.world, nc, self.rank, ep,
-                                           li, ri, lrow0 + k * rb if li >= 0 else 0)
+                                           li, ri, lrow0 + r_lo if li >= 0 else 0)
             done = torch.cuda.Event()
             done.record(main)
             d2h.wait_event(done)
             with torch.cuda.stream(d2h):
-                out_host[k * rb * per_out:(k + 1) * rb * per_out].copy_(ob, non_blocking=True)
+                out_host[r_lo * per_out:r_hi * per_out].copy_(ob, non_blocking=True)
         for st in (h2d, d2h) + tuple(ar.side):
             main.wait_stream(st)
         self.host_done = torch.cuda.Event()
