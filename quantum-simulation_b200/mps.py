@@ -46,7 +46,10 @@ class MPS(nn.Module):
     """Random right-canonical MPS with the orthogonality centre at site 0 (mps.py:21-70)."""
 
     def __init__(self, Nsites: int, chid: int, initial_bond_dim: int, device: Any, dtype: torch.dtype,
-                 seed: Optional[int] = None):
+                 seed: Optional[int] = None, *, rescale_carry: bool = False):
+        """Same positional signature as the reference.  ``rescale_carry=True`` (an extension, off by default so that the
+        tensors stay identical to the reference's) normalises the carry of the QR sweep at every site: the state is the
+        same ray, but long chains at large chi no longer end with a zero centre tensor (see the warning below)."""
         super().__init__()
         self.Nsites, self.chid = Nsites, chid
         self.device, self.dtype = device, dtype
@@ -55,6 +58,8 @@ class MPS(nn.Module):
         sites = random_mps(Nsites, chid, initial_bond_dim, dtype=dtype, device=device, seed=seed)
         for p in reversed(range(1, Nsites)):                # right-to-left QR sweep
             sites[p], carry = _absorb_right_factor(sites[p])
+            if rescale_carry:
+                carry = carry / torch.linalg.norm(carry)
             sites[p - 1] = torch.einsum("lsc,ck->lsk", sites[p - 1], carry)
         sites[0] = sites[0] / torch.linalg.norm(sites[0])
         # Same arithmetic as the reference (mps.py:57-60) -- including its failure mode: the carry is never rescaled,
@@ -66,7 +71,8 @@ class MPS(nn.Module):
             import warnings
             warnings.warn("MPS: the un-normalised canonicalisation carry over/underflowed (site 0 is zero or "
                           "non-finite), exactly as in the reference at this size; the first DMRG update will start from "
-                          "a vector drawn from the global RNG -- call torch.manual_seed(...) for a repeatable run",
+                          "a vector drawn from the global RNG -- call torch.manual_seed(...) for a repeatable run, or "
+                          "build the state with rescale_carry=True",
                           RuntimeWarning, stacklevel=2)
         ones = [torch.ones(1, device=device, dtype=dtype) for _ in range(Nsites + 1)]
         self._A = nn.ParameterList(_frozen(t) for t in sites)

@@ -239,3 +239,26 @@ def test_documented_binding_matches_the_header():
             m = re.compile(rf"\b{n}\b").search(body, at)
             assert m is not None, f"{cname}.{n} missing from (or out of order in) include/qsb200.h"
             at = m.end()
+
+
+def test_mps_long_chain_overflow_is_the_references_and_is_flagged():
+    """The reference's constructor never rescales the carry of its QR sweep (mps.py:52-60): on long chains the norm of
+    site 0 overflows and the centre tensor comes out zero / non-finite (L=100, chi=2048 in BASELINE config 3 -- the cause
+    of the run-to-run drift of the r01 sweep, profiles/r02_determinism.md).  The mirror reproduces that, warns, and offers
+    rescale_carry=True (same ray, finite centre)."""
+    import contextlib
+    import io
+    import warnings
+    with contextlib.redirect_stdout(io.StringIO()):
+        with pytest.warns(RuntimeWarning, match="global RNG"):
+            bad = qsb.MPS(300, 2, 64, "cpu", torch.float64, 1)
+        with warnings.catch_warnings():
+            warnings.simplefilter("error")
+            good = qsb.MPS(300, 2, 64, "cpu", torch.float64, 1, rescale_carry=True)
+            short = qsb.MPS(20, 2, 16, "cpu", torch.float64, 1)                 # no overflow, no warning
+    assert not bool(torch.isfinite(bad.B[0]).all()) or not bool(bad.B[0].any())
+    assert abs(float(torch.linalg.norm(good.B[0])) - 1.0) < 1e-12
+    for p in (1, 150, 299):                                                      # right-canonical away from the centre
+        b = good.B[p].reshape(good.B[p].shape[0], -1)
+        assert float(torch.linalg.norm(b @ b.T - torch.eye(b.shape[0], dtype=b.dtype))) < 1e-12
+    assert abs(float(torch.linalg.norm(short.B[0])) - 1.0) < 1e-12
