@@ -13,7 +13,8 @@ from .mps import MPS, random_mps
 from .eigensolver import lanczos_ground_state, clear_workspaces
 from .observables import (mpo_expectation, energy_expectation, energy_variance, local_expectation, two_point_correlation,
                           string_order_parameter, many_body_polarization, structure_factor, correlation_length,
-                          ground_state_fidelity, entanglement_entropy, entanglement_spectrum, product_expectation)
+                          ground_state_fidelity, entanglement_entropy, entanglement_spectrum, product_expectation,
+                          ground_state_energy, energy_density, excitation_gap, truncation_errors)
 from .dmrg import (ApplyMPO, LeftEnvUpdate, RightEnvUpdate, EnvironmentManager, Sweeps, DMRG,
                    set_contract_backend)
 
@@ -22,4 +23,4 @@ __all__ = ["MPS", "random_mps", "lanczos_ground_state", "clear_workspaces", "App
            "load_library", "mpo_expectation", "energy_expectation", "energy_variance", "local_expectation",
            "two_point_correlation", "string_order_parameter", "many_body_polarization", "structure_factor",
            "correlation_length", "ground_state_fidelity", "entanglement_entropy", "entanglement_spectrum",
-           "product_expectation"]
+           "product_expectation", "ground_state_energy", "energy_density", "excitation_gap", "truncation_errors"]

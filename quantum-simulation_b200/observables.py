@@ -34,7 +34,7 @@ from .dmrg import LeftEnvUpdate, RightEnvUpdate
 __all__ = ["mpo_expectation", "energy_expectation", "energy_variance", "squared_mpo", "local_expectation",
            "two_point_correlation", "string_order_parameter", "many_body_polarization", "structure_factor",
            "correlation_length", "ground_state_fidelity", "entanglement_entropy", "entanglement_spectrum",
-           "product_expectation"]
+           "product_expectation", "ground_state_energy", "energy_density", "excitation_gap", "truncation_errors"]
 
 
 def _site_tensors(mps: Any, form: str) -> List[torch.Tensor]:
@@ -446,3 +446,47 @@ def entanglement_entropy(mps: Any, bond: Optional[int] = None, eps: float = 1e-1
         p = p[p > eps]
         return float(-(p * torch.log(p)).sum())
     return [one(b) for b in range(len(mps.sWeight))] if bond is None else one(bond)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# host-side bookkeeping helpers of the reference's observables module (dmrg_observables.py:27-117, 209-233): no device
+# work, kept so that code written against that module runs unchanged
+# ------------------------------------------------------------------------------------------------------------------
+def _as_float(value: Any) -> float:
+    if isinstance(value, torch.Tensor):
+        if value.numel() != 1:
+            raise ValueError("Expected a scalar tensor.")
+        return float(value.detach().real.cpu().item())
+    return float(value.real) if isinstance(value, complex) else float(value)
+
+
+def ground_state_energy(energies: Any) -> float:
+    """Last entry of the energy trace ``DMRG.forward`` returns (dmrg_observables.py:51-76)."""
+    seq = energies.reshape(-1) if isinstance(energies, torch.Tensor) else energies
+    if len(seq) == 0:
+        raise ValueError("Energy trace is empty.")
+    return _as_float(seq[-1])
+
+
+def energy_density(energy: Any, num_sites: int) -> float:
+    """``energy / num_sites`` (dmrg_observables.py:79-94)."""
+    if num_sites <= 0:
+        raise ValueError("num_sites must be positive.")
+    return _as_float(energy) / int(num_sites)
+
+
+def excitation_gap(*args: Any, **kwargs: Any) -> float:
+    """Reserved by the reference for a future excited-state solver (dmrg_observables.py:97-117); same behaviour."""
+    raise NotImplementedError("Excitation gap requires excited-state DMRG or another E1 solver, "
+                              "which is not implemented yet.")
+
+
+def truncation_errors(dmrg_or_history: Any) -> List[float]:
+    """Discarded weights recorded after every two-site split (dmrg_observables.py:209-233)."""
+    from collections.abc import Mapping
+    history = dmrg_or_history.history if hasattr(dmrg_or_history, "history") else dmrg_or_history
+    if not isinstance(history, Mapping):
+        raise TypeError("Expected a DMRG object with .history or a history mapping.")
+    if "discarded_weights" not in history:
+        raise KeyError("history does not contain 'discarded_weights'.")
+    return [_as_float(v) for v in history["discarded_weights"]]

@@ -262,3 +262,22 @@ def test_mps_long_chain_overflow_is_the_references_and_is_flagged():
         b = good.B[p].reshape(good.B[p].shape[0], -1)
         assert float(torch.linalg.norm(b @ b.T - torch.eye(b.shape[0], dtype=b.dtype))) < 1e-12
     assert abs(float(torch.linalg.norm(short.B[0])) - 1.0) < 1e-12
+
+
+def test_host_side_observable_helpers():
+    """ground_state_energy / energy_density / truncation_errors / excitation_gap of the reference's observables module
+    (dmrg_observables.py:27-117, 209-233): no device work, same values and exception types."""
+    assert qsb.ground_state_energy([1.0, -2.5 + 0j]) == -2.5
+    assert qsb.ground_state_energy(torch.tensor([[3.0, 4.0]])) == 4.0
+    with pytest.raises(ValueError):
+        qsb.ground_state_energy([])
+    assert qsb.energy_density(torch.tensor(-8.0), 20) == -0.4
+    with pytest.raises(ValueError):
+        qsb.energy_density(1.0, 0)
+    assert qsb.truncation_errors({"discarded_weights": [1e-9, torch.tensor(2e-9)]}) == [1e-9, 2e-9]
+    with pytest.raises(KeyError):
+        qsb.truncation_errors({})
+    with pytest.raises(TypeError):
+        qsb.truncation_errors([1.0])
+    with pytest.raises(NotImplementedError):
+        qsb.excitation_gap()
