@@ -274,7 +274,7 @@ def test_host_side_observable_helpers():
     assert qsb.energy_density(torch.tensor(-8.0), 20) == -0.4
     with pytest.raises(ValueError):
         qsb.energy_density(1.0, 0)
-    assert qsb.truncation_errors({"discarded_weights": [1e-9, torch.tensor(2e-9)]}) == [1e-9, 2e-9]
+    assert qsb.truncation_errors({"discarded_weights": [1e-9, torch.tensor(2e-9, dtype=torch.float64)]}) == [1e-9, 2e-9]
     with pytest.raises(KeyError):
         qsb.truncation_errors({})
     with pytest.raises(TypeError):
