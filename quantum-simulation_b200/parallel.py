@@ -133,7 +133,6 @@ class SymmetricArena:
         # second half of the flag block: the (source rank x column block) grid of the host-resident path
         self.grid_cols = max(1, min(8, 32 // self.world))
         self.grid_flags = self.flags[32:]
-        self.grid_flag_ptrs = [self.ptrs[r] + 4 * (32 + self.rank * self.grid_cols) for r in range(self.world)]
         self.copy_streams = {"h2d": torch.cuda.Stream(device=device), "d2h": torch.cuda.Stream(device=device)}
         self.ticket = torch.zeros(1, dtype=torch.int32, device=device)
         self.side = [torch.cuda.Stream(device=device) for _ in range(2)]
@@ -276,11 +275,15 @@ class FusedShardedApplyMPO:
         h2d, d2h = ar.copy_streams["h2d"], ar.copy_streams["d2h"]
         nloc = self.chi_l * self.per_row // self.world
         rows = self.hi - self.lo
+        # column blocks: as many as the flag grid allows, each a whole number of GEMM tile columns (BN = 128 float64 /
+        # 64 complex128) -- every rank derives the same count from the same shape; 1 block = plain per-source gating
         nc = ar.grid_cols
-        if self.per_row % nc != 0:
-            raise ValueError("forward_host: per_row must be divisible by the number of column blocks")
+        bn = 64 if v_host.dtype.is_complex else 128
+        while nc > 1 and (self.per_row % nc != 0 or (self.per_row // nc) % bn != 0):
+            nc //= 2
         own = self.bufs[b][self.rank * nloc:(self.rank + 1) * nloc]
         own_flags = ar.grid_flags[self.rank * nc:(self.rank + 1) * nc]
+        peer_flag_ptrs = [ar.ptrs[r] + 4 * (32 + self.rank * nc) for r in range(self.world)]
         start = torch.cuda.Event()
         start.record(main)               # everything this buffer parity was used for two steps ago is behind `main`
         h2d.wait_event(start)
@@ -295,7 +298,7 @@ class FusedShardedApplyMPO:
             with torch.cuda.stream(side):
                 self._lib.push_columns_dma(own, rows, self.per_row, nc, own_flags,
                                            [self.dst_ptrs[b][r] for r in targets],
-                                           [ar.grid_flag_ptrs[r] for r in targets], ep)
+                                           [peer_flag_ptrs[r] for r in targets], ep)
         (li, lrow0), (ri, _r0) = self._lib.identity_of(L_rows), self._lib.identity_of(R)
         per_out = M1.shape[2] * M2.shape[2] * R.shape[1]
         out_dev = self._host_out(rows * per_out, v_host.dtype, dev)

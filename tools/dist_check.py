@@ -122,6 +122,31 @@ def main():
         t_host_serial = timeit(serial)
     except Exception as ex:
         host_note = repr(ex)[:300]
+    # host-resident path on a bond whose right dimension does not align with the GEMM tiles (chi_r = 100: the column
+    # blocks collapse to one per source rank) -- same result
+    host_ragged = -1.0
+    try:
+        cr = 100
+        g2 = torch.Generator(device=dev).manual_seed(23)
+        Lr = torch.randn(M1.shape[0], chi, chi, dtype=dtype, device=dev, generator=g2)
+        Rr = torch.randn(M2.shape[1], cr, cr, dtype=dtype, device=dev, generator=g2)
+        thr = torch.randn(chi * M1.shape[3] * M2.shape[3] * cr, dtype=dtype, device=dev, generator=g2)
+        for t_ in (Lr, Rr, thr):
+            dist.broadcast(torch.view_as_real(t_) if t_.is_complex() else t_, src=0)
+        pr = M1.shape[3] * M2.shape[3] * cr
+        refr = op1(thr, Lr, M1, M2, Rr)
+        fr = parallel.FusedShardedApplyMPO(chi, pr, dtype, dev)
+        hi_ = torch.empty((hi - lo) * pr, dtype=dtype).pin_memory()
+        ho_ = torch.empty((hi - lo) * M1.shape[2] * M2.shape[2] * cr, dtype=dtype).pin_memory()
+        hi_.copy_(thr[lo * pr: hi * pr].cpu())
+        for _ in range(3):
+            fr.forward_host(hi_, Lr[:, lo:hi, :].contiguous(), M1, M2, Rr, ho_)
+            torch.cuda.synchronize()
+            dist.barrier()
+        per_o = M1.shape[2] * M2.shape[2] * cr
+        host_ragged = float(torch.linalg.norm(ho_ - refr[lo * per_o: hi * per_o].cpu()) / torch.linalg.norm(refr))
+    except Exception as ex:
+        host_note = "ragged: " + repr(ex)[:250]
     # two-site split on the row shards against the single-GPU split of the same block
     split_res = {}
     try:
@@ -189,7 +214,7 @@ def main():
     herr = torch.tensor([host_err], dtype=torch.float64, device=dev)
     dist.all_reduce(herr, op=dist.ReduceOp.MAX)
     host_err = float(herr)
-    ok = ok and (host_note != "ok" or host_err <= 1e-12)
+    ok = ok and host_note == "ok" and host_err <= 1e-12 and 0.0 <= host_ragged <= 1e-12
     if split_res.get("accepted"):
         ok = ok and split_res["same_on_all_ranks"] and split_res["S2_maxdev_vs_gram"] <= 1e-13 and max(split_res["iso_dev"]) <= 1e-11
     if rank == 0:
@@ -200,7 +225,7 @@ def main():
                           "dmrg_max_rel_dev_per_update": float(errs[3]), "dmrg_bond_dims_equal": bool(errs[4] == 0.0),
                           "dmrg_s_single": t_single, "dmrg_s_sharded": t_shard, "dmrg_comm": d2.comm, "fused_matvec_rel_err": float(ferr),
                           "host_path_rel_err": host_err, "host_path_ms": t_host, "host_path_serial_ms": t_host_serial,
-                          "host_note": host_note, "sharded_split": split_res,
+                          "host_path_ragged_rel_err": host_ragged, "host_note": host_note, "sharded_split": split_res,
                           "fused_dma_ms": t_fused, "fused_sm_ms": t_fused_sm, "nccl_ms": t_nccl, "fused_note": fused_note, "ok": ok}))
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
