@@ -247,6 +247,10 @@ def _sketch_split(theta: torch.Tensor, maxdim: int, cutoff: float):
     Gs = 0.5 * (Gs + Gs.conj().T)
     lam, vecs = torch.linalg.eigh(Gs)
     lam = torch.flip(lam, dims=(0,)).clamp_min(0)
+    if TIMING:                                                 # diagnostics: how many directions carry weight above ...
+        csum = torch.cumsum(lam.flip(0), 0).flip(0) / lam.sum()          # tail weight from index j on
+        stats.setdefault("rank_tail_1e-15", []).append(int((csum > 1e-15).sum()))
+        stats.setdefault("rank_tail_1e-13", []).append(int((csum > 1e-13).sum()))
     S = torch.cat([torch.sqrt(lam), torch.sqrt(rho).reshape(1).to(rdt)])      # leading l values + the residual weight
     # the reference's truncation rule (dmrg.py:687-695) over the full spectrum: the total weight is known (|theta|^2)
     # and a cut beyond position l can only raise keep_cut above keep_max = k < l

@@ -175,7 +175,8 @@ def case_c3full():
              "E_mid_right": float(E[98]), "bond_dim_max": int(max(bd)), "updates_at_full_chi": int(sum(b == 2048 for b in bd)),
              "peak_memory_GB": torch.cuda.max_memory_allocated() / 1e9,
              "phase_seconds": dict(dm.timers) if dm.profile else None,
-             "split_paths": dict(__import__("quantum_simulation_b200").svd.stats),
+             "split_paths": {k_: (v_ if not isinstance(v_, list) else {"n": len(v_), "min": min(v_), "median": sorted(v_)[len(v_) // 2], "max": max(v_), "first10": v_[:10], "last10": v_[-10:]})
+                             for k_, v_ in __import__("quantum_simulation_b200").svd.stats.items()},
              "discarded_weight_max": float(max(dm.history["discarded_weights"])),
              "discarded_weight_max_full_chi": float(max(w for w, b in zip(dm.history["discarded_weights"], bd) if b == 2048))}]
 
