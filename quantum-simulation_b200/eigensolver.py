@@ -94,8 +94,11 @@ def _ensure_ws(n: int, k: int, device: torch.device, dtype: torch.dtype, vec) ->
 
 
 def clear_workspaces() -> None:
-    """Free every cached Lanczos workspace (the reference never evicts; at chi >= 2048 one is > 1 GB)."""
+    """Free every cached Lanczos workspace (the reference never evicts; at chi >= 2048 one is > 1 GB) and the cached
+    matrices of the two-site split's range compression."""
     _workspaces.clear()
+    from . import svd
+    svd.clear_caches()
 
 
 def _lanczos_impl(initial_vector, linear_operator, operator_args, num_restarts, krylov_dim, pro, pro_max_reorth,

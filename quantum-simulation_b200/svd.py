@@ -176,6 +176,14 @@ def _orthonormal_cols(Y: torch.Tensor, max_passes: int = 6, *, m_total: int = No
     return None
 
 
+def clear_caches() -> None:
+    """Free the cached test / regularisation matrices of the range compression (up to 8 matrices of n x l elements)
+    and forget the per-shape back-off state."""
+    _omega_cache.clear()
+    _backoff.clear()
+    _backoff_dist.clear()
+
+
 def _omega(n: int, l: int, dtype: torch.dtype, device: torch.device) -> torch.Tensor:
     """The fixed test matrix of the range compression: standard normal, generated once per (n, l, dtype, device) from
     its own seeded generator (no global RNG state is consumed; results repeat run to run)."""
