@@ -422,6 +422,64 @@ class _Env:
         self.t, self.sharded, self.chi = t, sharded, chi
 
 
+class _SiteStore:
+    """The site tensors of one canonical form (``mps.A`` or ``mps.B``), held either replicated (the reference's layout)
+    or -- ``sharded=True`` -- as this rank's ROW BLOCK over the left bond wherever that bond is shardable.  At
+    chi = 4096, d = 4, complex128 one site tensor is 1 GB and the 2 N replicated tensors of a 64-site chain would be
+    137 GB per GPU; row-sharded they are 17 GB, and a sweep only ever needs one full tensor (the right factor of theta /
+    the ket of an environment update) at a time, which is all-gathered on demand."""
+
+    def __init__(self, plist, owner: "ShardedDMRG"):
+        self.plist, self.o = plist, owner
+        self.left_dim = {}                  # p -> true left bond dimension of a tensor stored as a row block
+        self._cache = (None, None)          # (p, full tensor): the factor the last split produced is reused once
+
+    def is_sharded(self, p: int) -> bool:
+        return p in self.left_dim
+
+    def rows(self, p: int, lo: int, hi: int) -> torch.Tensor:
+        """Rows [lo, hi) of the left bond of site p -- this rank's own block when the tensor is stored sharded."""
+        t = self.plist[p].detach()
+        if self.is_sharded(p):
+            assert (lo, hi) == self.o._block(self.left_dim[p]), "a sharded site tensor only serves its own row block"
+            return t
+        return t[lo:hi]
+
+    def shape(self, p: int):
+        t = self.plist[p]
+        return (self.left_dim.get(p, t.shape[0]), t.shape[1], t.shape[2])
+
+    def full(self, p: int) -> torch.Tensor:
+        import torch.distributed as dist
+        t = self.plist[p].detach()
+        if not self.is_sharded(p):
+            return t
+        if self._cache[0] == p:
+            return self._cache[1]
+        l = self.left_dim[p]
+        out = torch.empty(l, t.shape[1], t.shape[2], dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out.view(-1), t.contiguous().view(-1), group=self.o.group)
+        self.o.comm["all_gather_site"] = self.o.comm.get("all_gather_site", 0) + 1
+        return out
+
+    def set(self, p: int, full: torch.Tensor, shard: bool) -> None:
+        import torch.nn as nn
+        l = full.shape[0]
+        if shard and self.o._shardable(l):
+            lo, hi = self.o._block(l)
+            self.plist[p] = nn.Parameter(full[lo:hi].contiguous(), requires_grad=False)
+            self.left_dim[p] = l
+            self._cache = (p, full)
+        else:
+            self.plist[p] = nn.Parameter(full, requires_grad=False)
+            self.left_dim.pop(p, None)
+            if self._cache[0] == p:
+                self._cache = (None, None)
+
+    def drop_cache(self) -> None:
+        self._cache = (None, None)
+
+
 class ShardedDMRG:
     """Two-site DMRG with the inner loop sharded over the left bond index across the ranks of ``group``.
 
@@ -444,7 +502,7 @@ class ShardedDMRG:
     """
 
     def __init__(self, mps, mpo, *, device, dtype=torch.float64, group=None, min_shard_chi: int = 64, engine=None,
-                 use_fused: bool = True):
+                 use_fused: bool = True, shard_mps: bool = False):
         import torch.distributed as dist
         from .dmrg import _as_mpo_list, _check_mpo_shapes
         self.group = group if group is not None else dist.group.WORLD
@@ -466,6 +524,13 @@ class ShardedDMRG:
         self._arena: Optional[SymmetricArena] = None
         self._max_chi = 0
         self.sharded_split = True       # two-site split on the row shards where the block allows it (svd.py)
+        # shard_mps: keep the MPS itself row-sharded over the left bonds (see _SiteStore); `mps.A` / `mps.B` then hold
+        # this rank's blocks until gather_mps() reassembles them
+        self.shard_mps = bool(shard_mps)
+        self._A, self._B = _SiteStore(mps.A, self), _SiteStore(mps.B, self)
+        prev = getattr(mps, "_qsb_row_sharded", None)
+        if prev is not None:            # an MPS left sharded by an earlier ShardedDMRG on the same group
+            self._A.left_dim, self._B.left_dim = dict(prev[0]), dict(prev[1])
         self.profile = False            # True: synchronise around the phases and accumulate seconds in self.timers
         self.timers = {"theta": 0.0, "gather_R": 0.0, "lanczos": 0.0, "split": 0.0, "env": 0.0}
         self.comm = {"all_gather_vec": 0, "all_gather_env": 0, "reduce_scatter_env": 0, "all_reduce_env": 0,
@@ -646,7 +711,7 @@ class ShardedDMRG:
     def _sweep(self, direction: str, L: list, R: list, params: dict, Ekeep: list) -> None:
         import torch.nn as nn
         mps, d, N = self.mps, self.chid, self.Nsites
-        A, B, sW = mps.A, mps.B, mps.sWeight
+        sW = mps.sWeight
         sites = range(N - 1) if direction == "right" else range(N - 2, -1, -1)
         kw = dict(num_restarts=params["maxit"], krylov_dim=params["krydim"], pro=params["reortho"],
                   pro_max_reorth=params["maxreortho"])
@@ -657,20 +722,21 @@ class ShardedDMRG:
         for p in sites:
             # theta build (dmrg.py:633-660).  On a sharded bond every rank builds only ITS rows of theta (the row block
             # of the left site tensor times the full right one): the sharded Lanczos solver takes exactly that shard
-            if direction == "right":
-                lt, rt, sw = B[p], B[p + 1], sW[p]
-            else:
-                lt, rt, sw = A[p], A[p + 1], sW[p + 2]
+            st = self._B if direction == "right" else self._A
+            sw = sW[p] if direction == "right" else sW[p + 2]
             if sw.dim() == 2:
                 sw = torch.diagonal(sw, 0)
-            l, s, m = lt.shape
+            l, s, m = st.shape(p)
+            rt = st.full(p + 1)                                  # the right factor is needed whole (one all-gather)
             _m, t, r = rt.shape
             chil, chir = l, r
             sharded = L[p].sharded
             lo, hi = self._block(chil) if sharded else (0, l)
             from .dmrg import build_theta
-            psi = build_theta(lt[lo:hi], rt, sw[lo:hi] if direction == "right" else sw, direction,
+            psi = build_theta(st.rows(p, lo, hi), rt, sw[lo:hi] if direction == "right" else sw, direction,
                               matmul=self.engine.matmul, fused=getattr(self.engine, "fused_scale", False))
+            del rt
+            st.drop_cache()
             self._tick("theta")
             R_full = self._tag(self._full(R[p + 2]))
             self._tick("gather_R")
@@ -689,13 +755,15 @@ class ShardedDMRG:
             self.history["sites"].append(int(p))
             sv = S[:keep]
             denom = sv.norm().add_(torch.finfo(sv.dtype).eps)
-            A[p] = nn.Parameter(Uk.reshape(chil, d, keep), requires_grad=False)
+            A_new, B_new = Uk.reshape(chil, d, keep), Vhk.reshape(keep, d, chir)
             sW[p + 1] = nn.Parameter(sv.div(denom), requires_grad=False)
-            B[p + 1] = nn.Parameter(Vhk.reshape(keep, d, chir), requires_grad=False)
             if direction == "right":
-                L[p + 1] = self._update_L(L[p], self.Ms[p], A[p])
+                L[p + 1] = self._update_L(L[p], self.Ms[p], A_new)
             else:
-                R[p + 1] = self._update_R(self.Ms[p + 1], R_full, B[p + 1])
+                R[p + 1] = self._update_R(self.Ms[p + 1], R_full, B_new)
+            self._A.set(p, A_new, self.shard_mps)               # stored whole or as this rank's row block
+            self._B.set(p + 1, B_new, self.shard_mps)
+            del A_new, B_new, Uk, Vhk
             self._tick("env")
             if params["dispon"] == 2 and self.rank == 0:
                 print(f"Sweep: {params['sweep_idx']} of {params['numsweeps']}, Loc: {p}, Energy: {Ekeep[-1]:.6f}")
@@ -732,7 +800,9 @@ class ShardedDMRG:
         L[0] = _Env(torch.ones(self.Ms[0].shape[0], 1, 1, device=self.device, dtype=self.dtype), False, 1)
         R[N] = _Env(torch.ones(self.Ms[-1].shape[1], 1, 1, device=self.device, dtype=self.dtype), False, 1)
         for p in range(N - 1, self.mps.ortho_center, -1):                          # dmrg.py:752-753
-            R[p] = self._update_R(self.Ms[p], self._full(R[p + 1]), self.mps.B[p])
+            R[p] = self._update_R(self.Ms[p], self._full(R[p + 1]), self._B.full(p))
+        if self.shard_mps:
+            self._shard_now()
         for k in range(1, sweeps.numsweeps + 1):
             params = {"chi": sweeps.maxdim[k - 1], "krydim": sweeps.krylov_dim[k - 1], "cutoff": sweeps.cutoff[k - 1],
                       "reortho": sweeps.reortho[k - 1], "maxreortho": sweeps.maxreortho[k - 1], "dispon": dispon,
@@ -742,10 +812,10 @@ class ShardedDMRG:
             sw = self.mps.sWeight[N - 1]                                            # dmrg.py:769-781
             if sw.dim() == 2:
                 sw = torch.diagonal(sw, 0)
-            Bl = self.mps.B[N - 1]
+            Bl = self._B.full(N - 1)
             U, S, Vh = self._boundary((sw.to(Bl.dtype).view(-1, 1, 1) * Bl).reshape(Bl.shape[0] * d, Bl.shape[2]))
             eps = torch.finfo(S.dtype).eps
-            self.mps.A[N - 1] = nn.Parameter(U.view(Bl.shape[0], d, Bl.shape[2]), requires_grad=False)
+            self._A.set(N - 1, U.view(Bl.shape[0], d, Bl.shape[2]), self.shard_mps)
             self.mps.sWeight[N] = nn.Parameter((S.unsqueeze(1) * Vh).to(self.dtype) / (S.norm().add_(eps)),
                                                requires_grad=False)
             self._sweep("left", L, R, params, Ekeep)
@@ -753,15 +823,37 @@ class ShardedDMRG:
             sw = self.mps.sWeight[1]                                                # dmrg.py:787-796
             if sw.dim() == 2:
                 sw = torch.diagonal(sw, 0)
-            A0 = self.mps.A[0] * sw.to(self.mps.A[0].dtype).view(1, 1, -1)
-            chil, _, chir = self.mps.A[0].shape
+            A0f = self._A.full(0)
+            A0 = A0f * sw.to(A0f.dtype).view(1, 1, -1)
+            chil, _, chir = A0f.shape
             U, S, Vh = self._boundary(A0.reshape(chil, d * chir))
-            self.mps.B[0] = nn.Parameter(Vh.view(chil, d, chir), requires_grad=False)
+            self._B.set(0, Vh.view(chil, d, chir), self.shard_mps)
             self.mps.sWeight[0] = nn.Parameter((U * S.unsqueeze(0)).to(self.dtype) / (S.norm().add_(eps)),
                                                requires_grad=False)
             if dispon == 1 and self.rank == 0:
                 print(f"Sweep: {k} of {sweeps.numsweeps}, Energy: {Ekeep[-1]:.12f}, "
                       f"Bond dim: {self.mps.A[N // 2].shape[-1]}")
+        self.mps._qsb_row_sharded = (dict(self._A.left_dim), dict(self._B.left_dim)) if self.shard_mps else None
         return Ekeep, self.mps
 
     __call__ = forward
+
+    def _shard_now(self) -> None:
+        """Replace every replicated site tensor whose left bond is shardable by this rank's row block."""
+        for store in (self._A, self._B):
+            for p in range(self.Nsites):
+                if not store.is_sharded(p):
+                    store.set(p, store.plist[p].detach(), True)
+            store.drop_cache()
+        if self.device is not None and torch.device(self.device).type == "cuda":
+            torch.cuda.empty_cache()
+
+    def gather_mps(self):
+        """Reassemble a row-sharded MPS (``shard_mps=True``) into the reference's replicated layout on every rank."""
+        for store in (self._A, self._B):
+            for p in range(self.Nsites):
+                if store.is_sharded(p):
+                    store.set(p, store.full(p), False)
+            store.drop_cache()
+        self.mps._qsb_row_sharded = None
+        return self.mps

@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--sites", type=int, default=0, help="use only the first/last sites of the MPO (0 = the full chain)")
     ap.add_argument("--profile", action="store_true")
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--shard-mps", action="store_true", help="keep the MPS itself row-sharded (ShardedDMRG(shard_mps=True))")
     args = ap.parse_args()
     rank, world, local = bench.dist_setup(0)
     dev = torch.device("cuda", local)
@@ -55,7 +56,7 @@ def main():
     t_init = time.perf_counter() - t0
     sw = qsb.Sweeps(1)
     sw.set_schedule(maxdim=[args.chi], cutoff=[0.0], krylov_dim=[4], noise=[0.0])
-    dm = parallel.ShardedDMRG(mps, mpo, device=dev, dtype=dtype)
+    dm = parallel.ShardedDMRG(mps, mpo, device=dev, dtype=dtype, shard_mps=args.shard_mps)
     dm.profile = args.profile
     before = dict(qsvd.stats)
     torch.manual_seed(1)
@@ -72,7 +73,9 @@ def main():
     bd = dm.history["bond_dims"]
     res = {"case": f"{desc}, {L} sites, d={d}, chi={args.chi}, {'c128' if dtype.is_complex else 'f64'}: one full two-site "
                    f"sweep through ShardedDMRG on {world} GPUs (MPO bonds up to {max(m.shape[1] for m in mpo)})",
-           "world": world, "sweep_s": float(t.item()), "bond_updates": len(E), "updates_at_full_chi": int(sum(b == args.chi for b in bd)),
+           "world": world, "mps_row_sharded": bool(args.shard_mps),
+           "mps_elements_stored_per_rank": int(sum(x.numel() for x in mps.A) + sum(x.numel() for x in mps.B)),
+           "sweep_s": float(t.item()), "bond_updates": len(E), "updates_at_full_chi": int(sum(b == args.chi for b in bd)),
            "mps_init_on_gpu_s": t_init, "E_end_of_sweep": float(E[-1]), "E_mid": float(E[len(E) // 2 - 1]),
            "peak_memory_gb_max_over_ranks": float(mem.item()), "comm": dm.comm,
            "split_paths": {k: qsvd.stats[k] - before.get(k, 0) for k in ("sketch_accepted", "sketch_rejected", "sketch_skipped", "gram", "svd")},
@@ -80,6 +83,8 @@ def main():
            "phase_seconds_rank0": dm.timers if args.profile else None}
     if not args.no_check:
         # independent check on rank 0: <H> of the final (replicated) MPS by plain left-environment contraction
+        if args.shard_mps:
+            dm.gather_mps()
         del dm
         qsb.clear_workspaces()
         torch.cuda.empty_cache()
