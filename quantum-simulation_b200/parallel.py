@@ -671,7 +671,9 @@ class ShardedDMRG:
         """Two-site split of the Lanczos result: on the row shards where the block allows it
         (``svd.sketch_split_sharded``: nobody gathers theta, only l x l matrices are reduced), else gathered and split on
         rank 0."""
-        from .svd import sharded_split_eligible, sketch_split_sharded
+        from . import svd as _svd
+        from .svd import sharded_split_eligible, sketch_split_sharded, gram_split_sharded
+        FAST_MIN = _svd.FAST_MIN
         d = self.chid
         m, n = chil * d, d * chir
         tried = False
@@ -680,6 +682,12 @@ class ShardedDMRG:
             out = sketch_split_sharded(v.view(m // self.world, n), m, chi, cutoff, self.group, self.comm)
             if out is not None:
                 self.comm["sharded_splits"] = self.comm.get("sharded_splits", 0) + 1
+                return out
+        if sharded and self.sharded_split and n <= m and m % self.world == 0 and min(m, n) >= FAST_MIN:
+            # real truncation (or no truncation at all): the exact Gram/eigh split, still without gathering theta
+            out = gram_split_sharded(v.view(m // self.world, n), m, chi, cutoff, self.group, self.comm)
+            if out is not None:
+                self.comm["sharded_gram_splits"] = self.comm.get("sharded_gram_splits", 0) + 1
                 return out
         theta = gather_rows(v, chil, d * d * chir, self.group) if sharded else v
         return self._split(theta.reshape(m, n), chi, cutoff, sketch=False if tried else None)

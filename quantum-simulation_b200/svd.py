@@ -44,7 +44,7 @@ from typing import Tuple
 
 import torch
 
-__all__ = ["two_site_split", "sketch_split_sharded", "sharded_split_eligible", "FAST_MIN"]
+__all__ = ["two_site_split", "sketch_split_sharded", "gram_split_sharded", "sharded_split_eligible", "FAST_MIN"]
 
 FAST_MIN = 256        # min(m, n) from which the Gram/eigh path is used
 SKETCH = True         # range compression in front of the Gram/eigh path for truncating blocks (module docstring)
@@ -245,7 +245,7 @@ def _sketch_split(theta: torch.Tensor, maxdim: int, cutoff: float):
         # captured range sharpens from ~(1 + k/p) tail to ~tail at the cost of two more orthonormalisations -- still
         # cheaper than the full eigenproblem, much cheaper than the gathered fallback of the sharded driver
         stats["sketch_refined"] = stats.get("sketch_refined", 0) + 1
-        V1 = orth(B.conj().T.contiguous() if theta.is_complex() else B.T.contiguous(), "reg2")      # n x l
+        V1 = orth(B.conj().T.resolve_conj().contiguous(), "reg2")      # n x l
         Q, B, rho = compress(_mm(theta, V1))
         stats["last_rho"] = float(rho / tot)
     if not stats["last_rho"] <= SKETCH_TOL:                    # (NaN-safe)
@@ -360,7 +360,7 @@ def sketch_split_sharded(theta_rows: torch.Tensor, m: int, maxdim: int, cutoff: 
         # subspace-iteration refinement, see _sketch_split: V = orth(B^H) with the rows of B^H (columns of theta) sharded
         stats["sketch_refined"] = stats.get("sketch_refined", 0) + 1
         Bh = B[:, c0:c0 + nc]
-        Bh = (Bh.conj().T if B.is_complex() else Bh.T).contiguous()           # this rank's nc rows of B^H (n x l)
+        Bh = Bh.conj().T.resolve_conj().contiguous()                          # this rank's nc rows of B^H (n x l)
         Vc = _orthonormal_cols(regularise(Bh, "reg2", n, c0), m_total=n, allsum=allsum, agree=agree)
         if Vc is None:
             return reject()
@@ -407,6 +407,71 @@ def sketch_split_sharded(theta_rows: torch.Tensor, m: int, maxdim: int, cutoff: 
     Vh = buf.permute(1, 0, 2).reshape(keep, n)
     stats["sketch_accepted"] += 1
     return U, S, Vh, keep
+
+
+def gram_split_sharded(theta_rows: torch.Tensor, m: int, maxdim: int, cutoff: float, group, comm: dict = None):
+    """The full Gram/eigh split (``_gram_split``, right-hand Gram matrix) on a ROW-SHARDED theta -- the exact path for
+    blocks whose truncation is real (the range compression rejects them) without gathering theta:
+
+      G   = sum_r theta_r^H theta_r            local GEMM + all-reduce (n x n)
+      eigh(G)                                  rank 0; spectrum and the leading eigenvectors V_k broadcast
+      Vh  = V_k^H                              replicated, rows orthonormal
+      (U S)_r = theta_r V_k                    local GEMM; columns orthogonal, norms S_j
+      U_r = orth_cols((U S)_r)                 CholeskyQR2 on the normalised columns, k x k Gram matrices all-reduced
+      U   = all-gather of the U_r
+
+    Requires n <= m (the smaller Gram matrix is the right-hand one) and m divisible by the world size.  Returns
+    ``(U, S, Vh, keep)`` replicated on every rank, or None (on every rank) if a Cholesky factorisation breaks down."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    mr, n = theta_rows.shape
+    assert mr * world == m and n <= m
+    dt, dev = theta_rows.dtype, theta_rows.device
+    rdt = theta_rows.real.dtype if theta_rows.is_complex() else dt
+
+    def allsum(t):
+        dist.all_reduce(torch.view_as_real(t) if t.is_complex() else t, group=group)
+        if comm is not None:
+            comm["all_reduce_split"] = comm.get("all_reduce_split", 0) + 1
+
+    def agree(flag: bool) -> bool:
+        f = torch.tensor([1.0 if flag else 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(f, op=dist.ReduceOp.MAX, group=group)
+        return bool(f.item() > 0)
+
+    G = _mm(theta_rows.T, theta_rows, conj_a=True)             # n x n partial
+    allsum(G)
+    src = dist.get_global_rank(group, 0)
+    meta = torch.zeros(1, dtype=torch.int64, device=dev)
+    S = torch.empty(n, dtype=rdt, device=dev)
+    if rank == 0:
+        G = 0.5 * (G + G.conj().T)
+        lam, vecs = torch.linalg.eigh(G)
+        S = torch.sqrt(torch.flip(lam, dims=(0,)).clamp_min(0)).contiguous()
+        meta[0] = _keep_from_spectrum(S, maxdim, cutoff)
+    del G
+    dist.broadcast(meta, src=src, group=group)
+    dist.broadcast(S, src=src, group=group)
+    keep = int(meta[0])
+    if rank == 0:
+        top = torch.flip(vecs[:, vecs.shape[1] - keep:], dims=(1,)).contiguous()        # n x keep
+        del vecs
+    else:
+        top = torch.empty(n, keep, dtype=dt, device=dev)
+    dist.broadcast(torch.view_as_real(top) if top.is_complex() else top, src=src, group=group)
+    if comm is not None:
+        comm["broadcast_split"] = comm.get("broadcast_split", 0) + 1
+    US = _mm(theta_rows, top)                                  # mr x keep
+    UrH = _orthonormal_rows(US.conj().T.resolve_conj().contiguous(), allsum=allsum, agree=agree)
+    if UrH is None:
+        return None
+    Ur = UrH.conj().T.resolve_conj().contiguous()
+    U = torch.empty(m, keep, dtype=dt, device=dev)
+    dist.all_gather_into_tensor(U.view(-1), Ur.view(-1), group=group)
+    if comm is not None:
+        comm["all_gather_split"] = comm.get("all_gather_split", 0) + 1
+    stats["gram_sharded"] = stats.get("gram_sharded", 0) + 1
+    return U, S, top.conj().T.resolve_conj().contiguous(), keep
 
 
 def _gram_split(theta: torch.Tensor, maxdim: int, cutoff: float):

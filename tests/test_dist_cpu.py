@@ -345,6 +345,7 @@ def test_sharded_dmrg_split_on_shards_and_noise(dtype_name, noise):
         assert len(E) == len(E1) and bonds == one[3]
         assert np.max(np.abs(E - E1) / np.abs(E1)) <= 1e-10
         assert comm.get("sharded_splits", 0) > 0 and comm["all_reduce_split"] > 0
+        assert comm.get("sharded_gram_splits", 0) > 0            # non-truncating / growing blocks: exact split on shards
         assert (comm.get("broadcast_noise", 0) > 0) == (noise > 0)
     assert two[0][1] == two[1][1]
 
@@ -415,3 +416,49 @@ def test_sharded_dmrg_with_row_sharded_mps(dtype_name):
         assert out["E2_shard"] == out["E2_full"]
         assert out["gathered"] >= stored_full * 0.9 and abs(out["norm_center"] - 1.0) < 1e-10
     assert res[0][1][True][0] == res[1][1][True][0]
+
+
+def _gram_split_worker(rank, world, port, dtype_name, m, n, k, cutoff, result_q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.set_num_threads(2)
+        from quantum_simulation_b200 import svd as qsvd
+        dtype = getattr(torch, dtype_name)
+        g = torch.Generator().manual_seed(13)
+        r = min(m, n)
+        U0, _ = torch.linalg.qr(torch.randn(m, r, dtype=dtype, generator=g))
+        V0, _ = torch.linalg.qr(torch.randn(n, r, dtype=dtype, generator=g))
+        sv = torch.exp(-torch.arange(r, dtype=torch.float64) * 0.05)          # slow decay: real truncation
+        theta = (U0 * sv.to(dtype)) @ V0.conj().T
+        theta = theta / torch.linalg.norm(theta)
+        mr = m // world
+        U, S, Vh, keep = qsvd.gram_split_sharded(theta[rank * mr:(rank + 1) * mr].contiguous(), m, k, cutoff,
+                                                 dist.group.WORLD, {})
+        Ue, Se, Vhe = torch.linalg.svd(theta, full_matrices=False)
+        kr = qsvd._keep_from_spectrum(Se, k, cutoff)
+        eye = torch.eye(keep, dtype=dtype)
+        best = (Ue[:, :kr] * Se[:kr].to(dtype)) @ Vhe[:kr]
+        result_q.put((rank, keep, kr, float(torch.linalg.norm(U.conj().T @ U - eye)),
+                      float(torch.linalg.norm(Vh @ Vh.conj().T - eye)), float((S[:keep] - Se[:keep]).abs().max()),
+                      float(torch.linalg.norm((U * S[:keep].to(dtype)) @ Vh - best)),
+                      abs(float((S[keep:] ** 2).sum()) - float((Se[keep:] ** 2).sum())),
+                      U.numpy().tobytes() + S.numpy().tobytes() + Vh.numpy().tobytes()))
+    except Exception:
+        import traceback
+        result_q.put(("error", rank, traceback.format_exc()))
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("dtype_name,world,shape,k,cutoff", [("float64", 2, (96, 96), 40, 0.0), ("complex128", 2, (128, 64), 30, 0.0),
+                                                             ("float64", 4, (128, 96), 10 ** 6, 1e-8)])
+def test_exact_gram_split_on_row_shards(dtype_name, world, shape, k, cutoff):
+    """svd.gram_split_sharded (the exact path for blocks with real truncation, theta never gathered): the reference's
+    keep, isometric factors, the optimally truncated block to 1e-7, identical factors on every rank."""
+    res = _spawn(_gram_split_worker, world, (dtype_name, shape[0], shape[1], k, cutoff))
+    for rank, keep, kr, du, dv, ds, drec, dw, blob in res:
+        assert keep == kr
+        assert du < 1e-12 and dv < 1e-12 and ds < 1e-9 and drec < 1e-7 and dw < 1e-13
+    assert len({r[8] for r in res}) == 1
