@@ -36,6 +36,7 @@ def run_gpu(key, L, chi, dtype, nsweeps, seed=1, krylov=4, maxit=2):
     sw.set_schedule(maxdim=[chi] * nsweeps, cutoff=[0.0] * nsweeps, krylov_dim=[krylov] * nsweeps,
                     noise=[0.0] * nsweeps)
     dm = quiet(qsb.DMRG, mps, [m.to(DEV) for m in mpo(key, dtype)], device=DEV, dtype=dtype)
+    dm.profile = "--profile" in sys.argv
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     E, _ = quiet(dm, sw, dispon=0, maxit=maxit)
@@ -90,6 +91,9 @@ def case_c2():
     torch.cuda.synchronize()
     t_obs = time.perf_counter() - t0
     res = {"case": "C2 TFIM L=100 g=0.5 chi=512, 10 sweeps", "mpo": key, "gpu_s": tg, "gpu_s_per_sweep": tg / 10,
+           "phase_seconds": dict(dm.timers) if dm.profile else None,
+           "split_paths": {k_: v_ for k_, v_ in __import__("quantum_simulation_b200").svd.stats.items() if not isinstance(v_, list)},
+           "launches": qsb.launch_counters(),
            "energy_by_environments": e_env, "variance_by_environments": var_env, "observables_s": t_obs,
            "E_final_gpu": float(Eg[-1]), "bond_dim_mid": dm.history["bond_dims"][-50],
            "E_end_of_sweep": [float(Eg[(k + 1) * 198 - 1]) for k in range(10)]}
