@@ -55,10 +55,14 @@ SKETCH_REG = 1e-9              # relative size of the regularising perturbation 
 SKETCH_REFINE_BELOW = 2e-11    # a rejected compression with rho below this gets one subspace-iteration refinement ...
 SKETCH_REFINE_SINGLE = False   # ... on row shards always (the gathered rank-0 fallback costs 3x more); on one GPU it
                                # measured as a wash against falling back (C3 sweep 36.4 -> 38.7 s with it), so it is off
+SKETCH_ADAPT = True            # rank-adaptive compression width (see _sketch_split): narrow sketch for over-resolved blocks
+SKETCH_TOL_NARROW = 1e-15      # accepted residual weight of a NARROW compression (the rest of the kept basis is padding)
+SKETCH_RANK_WEIGHT = 1e-17     # directions whose tail weight is below this do not count towards the numerical rank
 SKETCH_BACKOFF = 4             # after a rejected sketch: blocks of the same shape that skip it
 stats = {"sketch_accepted": 0, "sketch_rejected": 0, "sketch_skipped": 0, "gram": 0, "svd": 0, "last_rho": None}
 _omega_cache: dict = {}
 _backoff: dict = {}
+_rank_hint: dict = {}          # (m, n, k) -> numerical rank seen by the last accepted compression of that shape
 
 
 def _keep_from_spectrum(S: torch.Tensor, maxdim: int, cutoff: float) -> int:
@@ -182,6 +186,7 @@ def clear_caches() -> None:
     _omega_cache.clear()
     _backoff.clear()
     _backoff_dist.clear()
+    _rank_hint.clear()
 
 
 def _omega(n: int, l: int, dtype: torch.dtype, device: torch.device) -> torch.Tensor:
@@ -202,12 +207,33 @@ def _fixed_normal(tag: str, rows: int, cols: int, dtype: torch.dtype, device: to
     return t
 
 
-def _sketch_split(theta: torch.Tensor, maxdim: int, cutoff: float):
+def _complete_isometry(U1: torch.Tensor, c: int, tag: str) -> torch.Tensor:
+    """c more orthonormal columns, orthogonal to the orthonormal columns of U1 (m x r): a fixed Gaussian block with U1
+    projected out, CholeskyQR, once more ("twice is enough").  The padding of an over-resolved bond: directions that
+    carry no weight, only there because the reference's MPS has exactly ``maxdim`` columns."""
+    m = U1.shape[0]
+    X = _fixed_normal(tag, m, c, U1.dtype, U1.device, 0xC0DE).clone()
+    for _ in range(2):
+        X = X - _mm(U1, _mm(U1.T, X, conj_a=True))
+        Q = _orthonormal_cols(X)
+        X = Q if Q is not None else torch.linalg.qr(X)[0]
+    return X
+
+
+def _sketch_split(theta: torch.Tensor, maxdim: int, cutoff: float, _width: int = None):
     """Range compression + Gram/eigh of the compressed block (module docstring).  Returns None when the a-posteriori
-    bound rejects the compression (the caller falls back to the full Gram/eigh path)."""
+    bound rejects the compression (the caller falls back to the full Gram/eigh path).
+
+    Rank-adaptive width (``SKETCH_ADAPT``): the last accepted compression of a shape records the numerical rank r of
+    the block (directions beyond it carry < 1e-17 of the weight -- far below what any Gram method resolves).  The next
+    block of that shape is compressed to l1 = 1.5 r + 32 columns only; if theta has <= 1e-15 of its weight outside that
+    range, the l1 x l1 eigenproblem replaces the (maxdim + p)^2 one, and, when l1 < maxdim, the kept basis is padded
+    with weightless orthonormal directions (Schmidt values 0) up to the bond dimension the reference would keep.
+    An over-resolved run (TFIM at chi = 512: rank ~30) then pays for its rank, not for its bond dimension; otherwise
+    the narrow attempt is skipped (hint >= full width) or retried at full width."""
     m, n = theta.shape
     k = min(int(maxdim), m, n)
-    l = k + _oversample(k)
+    l_full = k + _oversample(k)
     if m > n:                                                  # compress the smaller side's partner: work on theta^H
         out = _sketch_split(theta.conj().T, maxdim, cutoff)
         if out is None:
@@ -215,7 +241,13 @@ def _sketch_split(theta: torch.Tensor, maxdim: int, cutoff: float):
         U, S, Vh, keep = out
         return Vh.conj().T.resolve_conj().contiguous(), S, U.conj().T.resolve_conj().contiguous(), keep
     rdt = theta.real.dtype if theta.is_complex() else theta.dtype
-    Y = _mm(theta, _omega(n, l, theta.dtype, theta.device))    # m x l
+    key = (m, n, k)
+    l = l_full if _width is None else _width
+    hint = _rank_hint.get(key)
+    if _width is None and SKETCH_ADAPT and hint is not None:
+        l = min(l_full, (max(64, int(1.5 * hint) + 32) + 63) // 64 * 64)
+    narrow = l < l_full
+    Y = _mm(theta, _omega(n, l_full, theta.dtype, theta.device)[:, :l])       # m x l
     # DMRG blocks are numerically rank-deficient (Schmidt values far below eps), which no Cholesky-based
     # orthogonalisation survives: `orth` lifts the null directions of Y to SKETCH_REG |Y| with a fixed Gaussian
     # perturbation.  range(Q) then contains the resolved directions of range(Y) up to angles ~SKETCH_REG / sigma_i, which
@@ -225,7 +257,7 @@ def _sketch_split(theta: torch.Tensor, maxdim: int, cutoff: float):
     def orth(Yc, tag):
         """Regularised shifted CholeskyQR of a tall matrix (Householder QR when a Cholesky pivot fails)."""
         if SKETCH_REG > 0:
-            Yc.add_(_fixed_normal(tag, Yc.shape[0], Yc.shape[1], theta.dtype, theta.device, 0xB200),
+            Yc.add_(_fixed_normal(tag, Yc.shape[0], l_full, theta.dtype, theta.device, 0xB200)[:, :Yc.shape[1]],
                     alpha=float(SKETCH_REG * torch.linalg.norm(Yc)) / (Yc.shape[0] * Yc.shape[1]) ** 0.5)
         Qc = _orthonormal_cols(Yc)
         if Qc is None:
@@ -240,6 +272,10 @@ def _sketch_split(theta: torch.Tensor, maxdim: int, cutoff: float):
         return Qc, Bc, torch.linalg.norm(theta - _mm(Qc, Bc)) ** 2      # (|theta|^2 - |B|^2 would cancel at 1e-14)
     Q, B, rho = compress(Y)
     stats["last_rho"] = float(rho / tot)
+    if narrow and not stats["last_rho"] <= SKETCH_TOL_NARROW:  # the block outgrew the hint: full width
+        stats["sketch_narrow_retry"] = stats.get("sketch_narrow_retry", 0) + 1
+        _rank_hint.pop(key, None)
+        return _sketch_split(theta, maxdim, cutoff, _width=l_full)
     if SKETCH_REFINE_SINGLE and SKETCH_TOL < stats["last_rho"] <= SKETCH_REFINE_BELOW:
         # marginal miss: one step of subspace iteration WITH re-orthonormalisation (V = orth(B^H), Y <- theta V): the
         # captured range sharpens from ~(1 + k/p) tail to ~tail at the cost of two more orthonormalisations -- still
@@ -255,21 +291,35 @@ def _sketch_split(theta: torch.Tensor, maxdim: int, cutoff: float):
     Gs = 0.5 * (Gs + Gs.conj().T)
     lam, vecs = torch.linalg.eigh(Gs)
     lam = torch.flip(lam, dims=(0,)).clamp_min(0)
+    tail = torch.cumsum(lam.flip(0), 0).flip(0) / tot          # weight carried from index j on
+    _rank_hint[key] = int((tail > SKETCH_RANK_WEIGHT).sum())
     if TIMING:                                                 # diagnostics: how many directions carry weight above ...
-        csum = torch.cumsum(lam.flip(0), 0).flip(0) / lam.sum()          # tail weight from index j on
-        stats.setdefault("rank_tail_1e-15", []).append(int((csum > 1e-15).sum()))
-        stats.setdefault("rank_tail_1e-13", []).append(int((csum > 1e-13).sum()))
+        stats.setdefault("rank_tail_1e-15", []).append(int((tail > 1e-15).sum()))
+        stats.setdefault("rank_tail_1e-13", []).append(int((tail > 1e-13).sum()))
+    if narrow:
+        stats["sketch_narrow"] = stats.get("sketch_narrow", 0) + 1
     S = torch.cat([torch.sqrt(lam), torch.sqrt(rho).reshape(1).to(rdt)])      # leading l values + the residual weight
     # the reference's truncation rule (dmrg.py:687-695) over the full spectrum: the total weight is known (|theta|^2)
     # and a cut beyond position l can only raise keep_cut above keep_max = k < l
-    keep = _keep_from_spectrum(S, k, cutoff)
-    top = torch.flip(vecs[:, vecs.shape[1] - keep:], dims=(1,))                # l x keep
-    U = _mm(Q, top)                                            # m x keep, orthonormal columns
-    Bk = _mm(top.T, B, conj_a=True)                            # keep x n : S_k Vh_k
+    if l > k:
+        keep = _keep_from_spectrum(S, k, cutoff)
+        pad = 0
+    else:                                                      # narrow compression: l <= k resolved directions
+        cut = _keep_from_spectrum(S, 10 ** 9, cutoff) if cutoff > 0.0 else l + 1
+        keep = cut if cut <= l else k                          # a cut beyond the resolved part keeps the full bond
+        pad = max(0, keep - l)
+    take = keep - pad
+    top = torch.flip(vecs[:, vecs.shape[1] - take:], dims=(1,))                 # l x take
+    U = _mm(Q, top)                                            # m x take, orthonormal columns
+    Bk = _mm(top.T, B, conj_a=True)                            # take x n : S_k Vh_k
     Vh = _orthonormal_rows(Bk) if USE_CHOLQR else None
     if Vh is None:
         Qc, Rr = torch.linalg.qr(Bk.conj().T)
         Vh = _fix_phase(Qc, Rr).conj().T
+    if pad:                                                    # weightless padding up to the reference's bond dimension
+        U = torch.cat([U, _complete_isometry(U, pad, "padU")], dim=1)
+        Vh = torch.cat([Vh, _complete_isometry(Vh.conj().T.resolve_conj().contiguous(), pad, "padV").conj().T], dim=0)
+        S = torch.cat([S[:take], torch.zeros(pad, dtype=rdt, device=S.device), S[-1:]])
     return U.resolve_conj().contiguous(), S, Vh.resolve_conj().contiguous(), keep
 
 

@@ -192,3 +192,39 @@ def test_sketched_split_refines_a_marginal_miss(dtype, monkeypatch):
     assert float((S[:64] ** 2 - Se[:64] ** 2).abs().max()) <= 2e-13
     eye = torch.eye(64, dtype=dtype)
     assert float(torch.linalg.norm(U.conj().T @ U - eye)) < 1e-12 and float(torch.linalg.norm(Vh @ Vh.conj().T - eye)) < 1e-12
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.complex128])
+@pytest.mark.parametrize("shape,cutoff", [((512, 512), 0.0), ((512, 640), 0.0), ((640, 512), 0.0), ((512, 512), 1e-12)])
+def test_rank_adaptive_compression_pads_an_over_resolved_bond(dtype, shape, cutoff, monkeypatch):
+    """An over-resolved block (numerical rank ~16, bond dimension 192): after the first split of the shape has recorded
+    the rank, the next ones are compressed to 64 columns only, the 64 x 64 eigenproblem replaces the 216 x 216 one and
+    the kept basis is padded with weightless orthonormal directions up to the reference's bond dimension -- same keep,
+    isometric factors, the optimally truncated block to the regularisation amplitude, exact discarded weight."""
+    from quantum_simulation_b200 import svd as qsvd
+    qsvd.clear_caches()
+    m, n = shape
+    theta, _ = _matrix(m, n, dtype, 1.2, seed=3)
+    theta = theta / torch.linalg.norm(theta)
+    Ue, Se, Vhe = torch.linalg.svd(theta, full_matrices=False)
+    before = qsvd.stats.get("sketch_narrow", 0)
+    for rep in range(3):
+        U, S, Vh, keep = two_site_split(theta, 192, cutoff, fast_min=1)
+    assert qsvd.stats.get("sketch_narrow", 0) == before + 2 and qsvd.stats["last_rho"] <= 1e-15
+    kr = _reference_keep(Se, 192, cutoff)
+    assert keep == kr and U.shape == (m, keep) and Vh.shape == (keep, n)
+    eye = torch.eye(keep, dtype=dtype)
+    assert float(torch.linalg.norm(U.conj().T @ U - eye)) < 1e-12
+    assert float(torch.linalg.norm(Vh @ Vh.conj().T - eye)) < 1e-12
+    best = (Ue[:, :kr] * Se[:kr].to(dtype)) @ Vhe[:kr]
+    assert float(torch.linalg.norm((U * S[:keep].to(dtype)) @ Vh - best)) < 1e-7
+    assert abs(float((S[keep:] ** 2).sum()) - float((Se[kr:] ** 2).sum())) <= 1e-15
+    assert float((S[:8] - Se[:8]).abs().max()) < 1e-13
+    # the block outgrows the hint: retried at full width, still right
+    wide, _ = _matrix(m, n, dtype, 0.12, seed=4)
+    wide = wide / torch.linalg.norm(wide)
+    r0 = qsvd.stats.get("sketch_narrow_retry", 0)
+    U, S, Vh, keep = two_site_split(wide, 192, cutoff, fast_min=1)
+    assert qsvd.stats.get("sketch_narrow_retry", 0) == r0 + 1
+    Sw = torch.linalg.svdvals(wide)
+    assert keep == _reference_keep(Sw, 192, cutoff) and float((S[:8] - Sw[:8]).abs().max()) < 1e-13
