@@ -799,17 +799,22 @@ def extras(args, qsb, _lib, dev, dtype, L, M1, M2, R, theta, peak_tf):
         th_dmrg = (U0 * sv.to(dtype)) @ V0.conj().T
         th_dmrg = th_dmrg / torch.linalg.norm(th_dmrg)
         del a_, U0, V0
-        qsvd._backoff.clear()
+        qsvd.clear_caches()
         before = dict(qsvd.stats)
+        adapt = qsvd.SKETCH_ADAPT
+        qsvd.SKETCH_ADAPT = False            # full-width compression: what a bond with numerical rank ~ chi costs
         t_s = timed(lambda: two_site_split(th_dmrg, chi, 0.0))
         took_sketch = qsvd.stats["sketch_accepted"] > before["sketch_accepted"]
+        qsvd.SKETCH_ADAPT = adapt            # rank-adaptive width: this synthetic block has numerical rank ~300
+        t_s_adapt = timed(lambda: two_site_split(th_dmrg, chi, 0.0), reps=3)
         th = theta.view(chi * d, d * chi)
         t_s_full = timed(lambda: two_site_split(th, chi, 0.0, sketch=False))
         del th_dmrg
         step = t_l + t_e + t_t + t_s
         out["bond_step"] = {"lanczos_8_matvecs_ms": t_l * 1e3, "env_update_ms": t_e * 1e3, "theta_build_ms": t_t * 1e3,
                             "two_site_split_ms": t_s * 1e3, "two_site_split_path": "range-compressed Gram/eigh" if took_sketch else "full Gram/eigh",
-                            "two_site_split_full_gram_ms": t_s_full * 1e3, "total_ms": step * 1e3,
+                            "two_site_split_full_gram_ms": t_s_full * 1e3,
+                            "two_site_split_rank_adaptive_ms": t_s_adapt * 1e3, "total_ms": step * 1e3,
                             "sweep_estimate_s": 2 * (100 - 1) * step,
                             "note": "bulk bond of Heisenberg L=100 at full chi; a sweep is 198 such steps (edge bonds "
                                     "are cheaper), so sweep_estimate_s is an upper estimate of the sweep time"}
