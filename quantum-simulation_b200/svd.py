@@ -209,15 +209,15 @@ def _fixed_normal(tag: str, rows: int, cols: int, dtype: torch.dtype, device: to
 
 def _complete_isometry(U1: torch.Tensor, c: int, tag: str) -> torch.Tensor:
     """c more orthonormal columns, orthogonal to the orthonormal columns of U1 (m x r): a fixed Gaussian block with U1
-    projected out, CholeskyQR, once more ("twice is enough").  The padding of an over-resolved bond: directions that
-    carry no weight, only there because the reference's MPS has exactly ``maxdim`` columns."""
+    projected out, orthonormalised (CholeskyQR; the projected Gaussian is well conditioned), U1 projected out once more
+    (an O(eps) correction that leaves the columns orthonormal to O(eps)).  The padding of an over-resolved bond:
+    directions that carry no weight, only there because the reference's MPS has exactly ``maxdim`` columns."""
     m = U1.shape[0]
-    X = _fixed_normal(tag, m, c, U1.dtype, U1.device, 0xC0DE).clone()
-    for _ in range(2):
-        X = X - _mm(U1, _mm(U1.T, X, conj_a=True))
-        Q = _orthonormal_cols(X)
-        X = Q if Q is not None else torch.linalg.qr(X)[0]
-    return X
+    X = _fixed_normal(tag, m, c, U1.dtype, U1.device, 0xC0DE)
+    X = X - _mm(U1, _mm(U1.T, X, conj_a=True))
+    Q = _orthonormal_cols(X)
+    X = Q if Q is not None else torch.linalg.qr(X)[0]
+    return X - _mm(U1, _mm(U1.T, X, conj_a=True))
 
 
 def _sketch_split(theta: torch.Tensor, maxdim: int, cutoff: float, _width: int = None):
