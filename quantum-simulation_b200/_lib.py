@@ -165,6 +165,21 @@ class nvtx_range:
         return False
 
 
+def row_block_bounds(rows: int, min_rows: int = 128, max_blocks: int = 5) -> list:
+    """Row blocks of a host-resident matvec's result, big first, small last: 1/2, 1/4, 1/8, ... of the rows while a
+    block stays >= ``min_rows`` (one GEMM tile row).  Every block's download overlaps the next block's compute, so only
+    the LAST, smallest download is exposed, at the price of few extra launches.  Returns the boundaries [0, ..., rows]."""
+    bounds = [0]
+    rest = int(rows)
+    while len(bounds) < max_blocks - 1 and rest % 2 == 0 and rest // 2 >= min_rows and rest > 2 * min_rows:
+        bounds.append(bounds[-1] + rest // 2)
+        rest -= rest // 2
+    if rest % 2 == 0 and rest // 2 >= min_rows:
+        bounds.append(bounds[-1] + rest // 2)
+    bounds.append(int(rows))
+    return bounds
+
+
 def status_string(code: int) -> str:
     return load().qsb_status_string(int(code)).decode()
 

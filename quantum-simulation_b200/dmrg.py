@@ -228,16 +228,7 @@ class ApplyMPO(_BaseContractModule):
         while row_chunks > 1 and (chi_li % (bk * row_chunks) != 0):
             row_chunks //= 2
         mode = "col" if col_chunks > 1 else ("row" if row_chunks > 1 else "plain")
-        # row blocks of the result: big first, small last (1/2, 1/4, 1/8, 1/8 of the rows while blocks stay >= 128 rows):
-        # every block's download overlaps the next block's compute, only the LAST download is exposed
-        bounds = [0]
-        rest = chi_lo
-        while len(bounds) < 4 and rest % 2 == 0 and rest // 2 >= 128 and rest > 256:
-            bounds.append(bounds[-1] + rest // 2)
-            rest -= rest // 2
-        if rest > 128 and rest % 2 == 0 and len(bounds) >= 2:
-            bounds.append(bounds[-1] + rest // 2)
-        bounds.append(chi_lo)
+        bounds = _lib.row_block_bounds(chi_lo)            # row blocks of the result, big first, small last
         main = torch.cuda.current_stream(dev)
         es = psi_host.element_size()
         with torch.cuda.device(dev):

@@ -302,16 +302,7 @@ class FusedShardedApplyMPO:
         (li, lrow0), (ri, _r0) = self._lib.identity_of(L_rows), self._lib.identity_of(R)
         per_out = M1.shape[2] * M2.shape[2] * R.shape[1]
         out_dev = self._host_out(rows * per_out, v_host.dtype, dev)
-        # row blocks of the result, big first, small last (1/2, 1/4, ... while blocks stay >= 128 rows): every block's
-        # download overlaps the next block's compute and only the last, smallest download stays exposed
-        bounds = [0]
-        rest = rows
-        while len(bounds) < 4 and rest % 2 == 0 and rest // 2 >= 128 and rest > 256:
-            bounds.append(bounds[-1] + rest // 2)
-            rest -= rest // 2
-        if rest > 128 and rest % 2 == 0:
-            bounds.append(bounds[-1] + rest // 2)
-        bounds.append(rows)
+        bounds = self._lib.row_block_bounds(rows)          # row blocks of the result, big first, small last
         for r_lo, r_hi in zip(bounds[:-1], bounds[1:]):
             Lb = L_rows[:, r_lo:r_hi, :]
             ob = out_dev[r_lo * per_out:r_hi * per_out]

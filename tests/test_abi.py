@@ -281,3 +281,20 @@ def test_host_side_observable_helpers():
         qsb.truncation_errors([1.0])
     with pytest.raises(NotImplementedError):
         qsb.excitation_gap()
+
+
+def test_row_block_bounds_of_the_host_pipelines():
+    """Result row blocks of the host-resident matvecs (ApplyMPO._forward_host, FusedShardedApplyMPO.forward_host): a
+    partition of the rows, halving sizes, never below one GEMM tile row, at most 5 blocks."""
+    from quantum_simulation_b200 import _lib
+    assert _lib.row_block_bounds(2048) == [0, 1024, 1536, 1792, 1920, 2048]
+    assert _lib.row_block_bounds(1024) == [0, 512, 768, 896, 1024]
+    assert _lib.row_block_bounds(256) == [0, 128, 256]
+    assert _lib.row_block_bounds(128) == [0, 128] and _lib.row_block_bounds(130) == [0, 130]
+    assert _lib.row_block_bounds(1) == [0, 1] and _lib.row_block_bounds(96) == [0, 96]
+    for rows in (64, 200, 384, 512, 640, 4096, 6144):
+        b = _lib.row_block_bounds(rows)
+        sizes = [y - x for x, y in zip(b[:-1], b[1:])]
+        assert b[0] == 0 and b[-1] == rows and sum(sizes) == rows and len(sizes) <= 5
+        assert all(s >= 128 for s in sizes) or len(sizes) == 1
+        assert sizes == sorted(sizes, reverse=True)
